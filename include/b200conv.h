@@ -1,0 +1,122 @@
+/*
+ * b200conv.h — C ABI of the B200-native partitioned-convolution engine.
+ *
+ * Drop-in boundary for the hot path of tiagolr/reevr (REEV-R): everything behind
+ *   fftconvolver::FFTConvolver::{init,process,clear,reset}          libs/FFTConvolver/FFTConvolver.h:62-80
+ *   fftconvolver::TwoStageFFTConvolver::{init,process,reset,clear}  libs/FFTConvolver/TwoStageFFTConvolver.h:65-83
+ *   StereoConvolver::{loadImpulse,process,reset,clear}              src/dsp/StereoConvolver.h:20-25
+ * i.e. AudioFFT::fft/ifft (AudioFFT.h:135-158), ComplexMultiplyAccumulate / Sum (Utilities.h:319-344)
+ * and the frequency-domain delay line they operate on.  Plain C: opaque handle, raw pointers
+ * and sizes only, no C++/torch types, never throws.  One handle = C independent mono
+ * convolvers ("channels", each with its own impulse response) that share the block schedule
+ * and are processed by the same kernel launches (C = 1 reproduces one reference object;
+ * C = 2 / 4 reproduces one StereoConvolver in stereo / quad mode).
+ *
+ * Status codes: 0 = ok, negative = error (message via b200conv_last_error).  There is NO CPU
+ * fall-back: if CUDA is unavailable every call fails loudly with B200CONV_ECUDA.
+ *
+ * Threading contract = the reference's (FFTConvolver.h:44-47): one caller at a time per
+ * handle; different handles are fully independent (own streams, own device arena).
+ */
+#ifndef B200CONV_H
+#define B200CONV_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CONV_OK        0
+#define B200CONV_EINVAL   -1   /* bad argument (e.g. block size 0 — the reference's init()==false) */
+#define B200CONV_ECUDA    -2   /* CUDA runtime error / no device */
+#define B200CONV_ESTATE   -3   /* call not valid in this state */
+#define B200CONV_ENOMEM   -4
+
+typedef struct b200conv b200conv_t;
+
+typedef struct b200conv_config {
+  int n_channels;        /* C >= 1 mono convolvers in this handle                                  */
+  int device;            /* CUDA device ordinal                                                     */
+  int max_batch_blocks;  /* head-stage blocks processed per internal launch group (0 = default 4736) */
+  int shard_rank;        /* partition-range shard owned by this handle (multi-GPU), 0 <= rank < n   */
+  int shard_count;       /* number of shards (1 = unsharded)                                        */
+  int cmac_variant;      /* 0 = auto; >0 selects a specific CMAC kernel variant (tuning/bench)      */
+} b200conv_config;
+
+/* Lifetime ------------------------------------------------------------------------------- */
+b200conv_t* b200conv_create(const b200conv_config* cfg);     /* NULL only if cfg is invalid/OOM */
+void        b200conv_destroy(b200conv_t* h);
+const char* b200conv_last_error(const b200conv_t* h);         /* "" if none                      */
+
+/* IR load (replaces FFTConvolver::init FFTConvolver.cpp:93-152 and
+ * TwoStageFFTConvolver::init TwoStageFFTConvolver.cpp:87-148).  ir[c] points to ir_len[c]
+ * float32 taps of channel c (host memory, copied during the call).  Same semantics as the
+ * reference: trailing taps with |h| < 1e-6 are trimmed, block sizes are rounded up to a power
+ * of two, an empty IR is legal (process() then writes zeros), block size 0 -> B200CONV_EINVAL. */
+int b200conv_init_uniform(b200conv_t* h, size_t block, const float* const* ir, const size_t* ir_len);
+int b200conv_init_twostage(b200conv_t* h, size_t head_block, size_t tail_block,
+                           const float* const* ir, const size_t* ir_len);
+/* Non-uniform schedule (beyond the reference): stage s uses block size blocks[s] for the taps
+ * [offsets[s], offsets[s+1]) (offsets[0] = 0, last stage runs to the end of the IR).  Stage 0
+ * is the zero-latency head; for s >= 1 offsets[s] must be a multiple of blocks[s] and >= blocks[s]. */
+int b200conv_init_stages(b200conv_t* h, int n_stages, const size_t* blocks, const size_t* offsets,
+                         const float* const* ir, const size_t* ir_len);
+
+/* Streaming convolution (replaces FFTConvolver::process FFTConvolver.cpp:155-212 and
+ * TwoStageFFTConvolver::process TwoStageFFTConvolver.cpp:151-233): in[c] / out[c] are HOST
+ * pointers to `len` float32 samples per channel; any len >= 0, zero added latency, output is
+ * complete on return.  in/out may not alias (same rule as the reference).
+ * Long calls are internally cut into block batches and pipelined over PCIe. */
+int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, size_t len);
+
+/* Same, with DEVICE-resident buffers: channel c at in_dev + c*in_stride (floats).  Asynchronous
+ * on the handle's stream unless sync != 0.  This is the throughput path bench.py times. */
+int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride,
+                            float* out_dev, size_t out_stride, size_t len, int sync);
+
+/* FFTConvolver::clear (FFTConvolver.cpp:80-90) / TwoStageFFTConvolver::clear (:69-84): forget
+ * all audio history, keep the IR.  Implemented as a TRUE clear (also mid-block), see DESIGN.md. */
+int b200conv_clear(b200conv_t* h);
+/* FFTConvolver::reset (FFTConvolver.cpp:56-78): drop the IR and all device memory. */
+int b200conv_reset(b200conv_t* h);
+
+/* Introspection --------------------------------------------------------------------------- */
+typedef struct b200conv_stage_info {
+  size_t block;        /* B_s                                  */
+  size_t partitions;   /* P_s (max over channels, post-trim)    */
+  size_t tap_offset;   /* first IR tap handled by this stage     */
+  size_t p_begin;      /* partition range owned by this shard    */
+  size_t p_end;
+} b200conv_stage_info;
+int    b200conv_num_stages(const b200conv_t* h);
+int    b200conv_stage(const b200conv_t* h, int s, b200conv_stage_info* out);
+size_t b200conv_ir_len(const b200conv_t* h, int channel);    /* post-trim tap count            */
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+unsigned long long b200conv_launch_count(const b200conv_t* h);
+/* Device time (ms) spent in the dominant CMAC kernel / all kernels during the last
+ * b200conv_process_device call, measured with CUDA events on the handle's stream
+ * (enabled by b200conv_set_timing(h, 1); adds two event records per kernel). */
+int    b200conv_set_timing(b200conv_t* h, int enable);
+int    b200conv_last_timing(const b200conv_t* h, float* cmac_ms, float* fft_ms, float* ifft_ms,
+                            int* cmac_launches);
+void*  b200conv_stream(const b200conv_t* h);                  /* cudaStream_t of the head path  */
+
+/* Multi-GPU partition-range sharding: with shard_count > 1 every handle computes
+ * the partial spectrum sum over its own partition range; between the CMAC sweep and the
+ * inverse FFT the engine calls `reduce(user, dev_ptr, n_floats, stream)` which must sum the
+ * buffer over all shards into shard 0 (ncclReduce on that stream).  Only shard 0 produces output. */
+typedef int (*b200conv_reduce_fn)(void* user, float* dev_buf, size_t n_floats, void* cuda_stream);
+int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
+
+/* Pinned host memory helpers (staging buffers for the e2e path). */
+void* b200conv_alloc_host(size_t bytes);
+void  b200conv_free_host(void* p);
+
+/* Version / build info string ("b200conv x.y sm_100a ..."). */
+const char* b200conv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CONV_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/b200conv.h.
+
+The product path has no CPU fall-back: if libb200conv.so is missing or cannot be loaded this
+module raises, it never substitutes another implementation.  (`load(path)` exists so that the
+test-suite can bind the same ABI of the CPU *emulation* build under tests/emu — test
+infrastructure only, never used by this package on its own.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200conv.so")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int),
+        ("device", C.c_int),
+        ("max_batch_blocks", C.c_int),
+        ("shard_rank", C.c_int),
+        ("shard_count", C.c_int),
+        ("cmac_variant", C.c_int),
+    ]
+
+
+class StageInfo(C.Structure):
+    _fields_ = [
+        ("block", C.c_size_t),
+        ("partitions", C.c_size_t),
+        ("tap_offset", C.c_size_t),
+        ("p_begin", C.c_size_t),
+        ("p_end", C.c_size_t),
+    ]
+
+
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+# every symbol include/b200conv.h declares: (name, restype, argtypes)
+_PP = C.POINTER(C.c_void_p)
+SYMBOLS = [
+    ("b200conv_create", C.c_void_p, [C.POINTER(Config)]),
+    ("b200conv_destroy", None, [C.c_void_p]),
+    ("b200conv_last_error", C.c_char_p, [C.c_void_p]),
+    ("b200conv_init_uniform", C.c_int, [C.c_void_p, C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
+    ("b200conv_init_twostage", C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _PP, C.POINTER(C.c_size_t)]),
+    ("b200conv_init_stages", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _PP, C.POINTER(C.c_size_t)]),
+    ("b200conv_process", C.c_int, [C.c_void_p, _PP, _PP, C.c_size_t]),
+    ("b200conv_process_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
+    ("b200conv_clear", C.c_int, [C.c_void_p]),
+    ("b200conv_reset", C.c_int, [C.c_void_p]),
+    ("b200conv_num_stages", C.c_int, [C.c_void_p]),
+    ("b200conv_stage", C.c_int, [C.c_void_p, C.c_int, C.POINTER(StageInfo)]),
+    ("b200conv_ir_len", C.c_size_t, [C.c_void_p, C.c_int]),
+    ("b200conv_launch_count", C.c_ulonglong, [C.c_void_p]),
+    ("b200conv_set_timing", C.c_int, [C.c_void_p, C.c_int]),
+    ("b200conv_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    ("b200conv_stream", C.c_void_p, [C.c_void_p]),
+    ("b200conv_set_reduce", C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
+    ("b200conv_alloc_host", C.c_void_p, [C.c_size_t]),
+    ("b200conv_free_host", None, [C.c_void_p]),
+    ("b200conv_version", C.c_char_p, []),
+]
+
+
+def load(path: str | None = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build the CUDA extension first (python -m reevr_b200.build); "
+            "there is no CPU fall-back")
+    lib = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_default = None
+
+
+def default() -> C.CDLL:
+    global _default
+    if _default is None:
+        _default = load()
+    return _default

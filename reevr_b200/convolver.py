@@ -1,0 +1,216 @@
+"""Python mirror of the reference's convolver surface on top of the C ABI (tests / bench glue).
+
+Class and method names follow the reference:
+  FFTConvolver          libs/FFTConvolver/FFTConvolver.h:62-80         init / process / clear / reset
+  TwoStageFFTConvolver  libs/FFTConvolver/TwoStageFFTConvolver.h:65-83 init / process / reset / clear
+  StereoConvolver       src/dsp/StereoConvolver.h:20-30                prepare / loadImpulse / process / reset / clear
+`Engine` is the multi-channel handle underneath (one launch set for C channels).
+The C++ drop-in classes for the JUCE host live in include/FFTConvolver.h and
+include/TwoStageFFTConvolver.h; this module exists because the test-suite and bench are Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class B200ConvError(RuntimeError):
+    pass
+
+
+def _ptr_array(arrs: Sequence[np.ndarray]):
+    arr = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+class Engine:
+    """C mono convolvers in one handle (b200conv_t)."""
+
+    def __init__(self, n_channels: int = 1, device: int = 0, max_batch_blocks: int = 0,
+                 shard_rank: int = 0, shard_count: int = 1, cmac_variant: int = 0, lib=None):
+        self._l = lib or _lib.default()
+        cfg = _lib.Config(n_channels, device, max_batch_blocks, shard_rank, shard_count, cmac_variant)
+        self._h = self._l.b200conv_create(C.byref(cfg))
+        if not self._h:
+            raise B200ConvError("b200conv_create failed")
+        self.n_channels = n_channels
+        self._reduce_cb = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str, allow_einval: bool = False) -> int:
+        if rc == 0 or (allow_einval and rc == -1):
+            return rc
+        raise B200ConvError(f"{what} failed ({rc}): {self._l.b200conv_last_error(self._h).decode()}")
+
+    def _irs(self, irs):
+        irs = [np.ascontiguousarray(a, dtype=np.float32) for a in irs]
+        if len(irs) != self.n_channels:
+            raise ValueError("need one IR per channel")
+        keep = [a if a.size else np.zeros(1, np.float32) for a in irs]
+        lens = (C.c_size_t * len(irs))(*[a.size for a in irs])
+        return keep, _ptr_array(keep), lens
+
+    # -- IR load ---------------------------------------------------------------------------
+    def init_uniform(self, block: int, irs) -> bool:
+        keep, ptrs, lens = self._irs(irs)
+        return self._check(self._l.b200conv_init_uniform(self._h, block, ptrs, lens), "init_uniform", True) == 0
+
+    def init_twostage(self, head: int, tail: int, irs) -> bool:
+        keep, ptrs, lens = self._irs(irs)
+        return self._check(self._l.b200conv_init_twostage(self._h, head, tail, ptrs, lens), "init_twostage", True) == 0
+
+    def init_stages(self, blocks, offsets, irs) -> bool:
+        keep, ptrs, lens = self._irs(irs)
+        b = (C.c_size_t * len(blocks))(*blocks)
+        o = (C.c_size_t * len(offsets))(*offsets)
+        return self._check(self._l.b200conv_init_stages(self._h, len(blocks), b, o, ptrs, lens), "init_stages", True) == 0
+
+    # -- processing ------------------------------------------------------------------------
+    def process(self, xs) -> list:
+        """xs: C arrays of equal length (host). Returns C float32 arrays."""
+        xs = [np.ascontiguousarray(a, dtype=np.float32) for a in xs]
+        n = xs[0].size
+        if any(a.size != n for a in xs) or len(xs) != self.n_channels:
+            raise ValueError("need one equally long input per channel")
+        ys = [np.empty(max(n, 1), np.float32)[:n] for _ in xs]
+        if n:
+            self._check(self._l.b200conv_process(self._h, _ptr_array(xs), _ptr_array(ys), n), "process")
+        return ys
+
+    def process_into(self, in_ptrs, out_ptrs, n: int) -> None:
+        """Raw host pointers (ctypes arrays of void*), e.g. pinned staging buffers."""
+        self._check(self._l.b200conv_process(self._h, in_ptrs, out_ptrs, n), "process")
+
+    def process_device(self, in_ptr: int, in_stride: int, out_ptr: int, out_stride: int, n: int, sync: bool = False):
+        self._check(self._l.b200conv_process_device(self._h, in_ptr, in_stride, out_ptr, out_stride, n, int(sync)),
+                    "process_device")
+
+    def clear(self):
+        self._check(self._l.b200conv_clear(self._h), "clear")
+
+    def reset(self):
+        self._check(self._l.b200conv_reset(self._h), "reset")
+
+    # -- introspection ---------------------------------------------------------------------
+    def stages(self) -> list:
+        out = []
+        for s in range(self._l.b200conv_num_stages(self._h)):
+            info = _lib.StageInfo()
+            self._l.b200conv_stage(self._h, s, C.byref(info))
+            out.append(dict(block=info.block, partitions=info.partitions, tap_offset=info.tap_offset,
+                            p_begin=info.p_begin, p_end=info.p_end))
+        return out
+
+    def ir_len(self, c: int = 0) -> int:
+        return int(self._l.b200conv_ir_len(self._h, c))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._l.b200conv_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._l.b200conv_stream(self._h) or 0)
+
+    def set_timing(self, on: bool):
+        self._l.b200conv_set_timing(self._h, int(on))
+
+    def last_timing(self) -> dict:
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        self._l.b200conv_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n))
+        return dict(cmac_ms=a.value, fft_ms=b.value, ifft_ms=c.value, cmac_launches=n.value)
+
+    def set_reduce(self, fn):
+        """fn(dev_ptr:int, n_floats:int, stream:int) -> int (0 = ok); sums the buffer into shard 0."""
+        def tramp(_user, ptr, n, stream):
+            try:
+                return int(fn(int(ptr), int(n), int(stream or 0)) or 0)
+            except Exception:  # never raise through the C ABI
+                import traceback
+                traceback.print_exc()
+                return -1
+        self._reduce_cb = _lib.REDUCE_FN(tramp)
+        self._l.b200conv_set_reduce(self._h, self._reduce_cb, None)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.b200conv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FFTConvolver:
+    """Uniform partitioned convolver, one channel (reference: FFTConvolver.h:62-80)."""
+
+    def __init__(self, **kw):
+        self._e = Engine(1, **kw)
+
+    def init(self, blockSize: int, ir) -> bool:
+        return self._e.init_uniform(blockSize, [ir])
+
+    def process(self, x) -> np.ndarray:
+        return self._e.process([x])[0]
+
+    def clear(self):
+        self._e.clear()
+
+    def reset(self):
+        self._e.reset()
+
+
+class TwoStageFFTConvolver(FFTConvolver):
+    """Head/tail convolver, one channel (reference: TwoStageFFTConvolver.h:65-83)."""
+
+    def init(self, headBlockSize: int, tailBlockSize: int, ir) -> bool:  # type: ignore[override]
+        return self._e.init_twostage(headBlockSize, tailBlockSize, [ir])
+
+
+class StereoConvolver:
+    """LL/RR (+LR/RL in quad mode) convolvers of src/dsp/StereoConvolver.{h,cpp} as ONE handle."""
+
+    def __init__(self, **kw):
+        self._kw = kw
+        self._e = None
+        self.isQuad = False
+        self.headBlockSize = 0
+        self.tailBlockSize = 0
+        self.size = 0
+
+    def prepare(self, samplesPerBlock: int):          # StereoConvolver.cpp:8-20
+        self.size = samplesPerBlock
+        h = 1
+        while h < samplesPerBlock:
+            h *= 2
+        self.headBlockSize = h
+        self.tailBlockSize = max(8192, 2 * h)
+
+    def loadImpulse(self, irLL, irRR, irLR=None, irRL=None):   # StereoConvolver.cpp:22-31
+        self.isQuad = irLR is not None and irRL is not None
+        irs = [irLL, irRR] + ([irLR, irRL] if self.isQuad else [])
+        if self._e is None or self._e.n_channels != len(irs):
+            self._e = Engine(len(irs), **self._kw)
+        return self._e.init_twostage(self.headBlockSize, self.tailBlockSize, irs)
+
+    def process(self, dataL, dataR):                   # StereoConvolver.cpp:33-42
+        """Returns (bufferLL, bufferRR[, bufferLR, bufferRL])."""
+        xs = [dataL, dataR] + ([dataL, dataR] if self.isQuad else [])
+        return tuple(self._e.process(xs))
+
+    def clear(self):
+        if self._e:
+            self._e.clear()
+
+    def reset(self):
+        if self._e:
+            self._e.reset()

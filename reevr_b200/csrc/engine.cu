@@ -1,0 +1,735 @@
+// engine.cu — host side of the B200 partitioned-convolution engine + the C ABI (include/b200conv.h).
+//
+// One handle = C mono convolvers sharing a stage schedule.  Stage s = uniform partitioned
+// convolver with block B_s over the IR taps [off_s, off_{s+1}) whose contribution is delayed by
+// q_s = off_s / B_s blocks (the scheme TwoStageFFTConvolver.cpp:120-138,166-222 uses for its
+// tails, generalised): stage 0 is the zero-latency head (handles partially filled blocks like
+// FFTConvolver.cpp:164-193), stages >= 1 work on completed blocks only and deposit their
+// output into a look-ahead ring the head's inverse-FFT epilogue adds on top.
+//
+// Device state per stage (all float32 / float2, resident for the handle's lifetime):
+//   H   [C][Prows][B]   IR partition spectra (this shard's partition range), zero padded
+//   X   [C][R][B]       input-spectrum timeline = the frequency-domain delay line, linear:
+//                       row `head` is the open block; partition p of output block t reads row
+//                       head + t - p.  Compacted (history moved to the front) when full.
+//   Y   [1+T][C][B]     spectra of the current batch; row 0 = last completed block of the
+//                       previous batch (the overlap state, FFTConvolver.cpp:204 kept in the
+//                       frequency domain)
+//   inbuf [C][B + Lmax] time-domain input of the open block + this call's samples
+//   fut [C][ring]       (stages >= 1) look-ahead output ring, indexed by absolute position
+#if defined(PC_EMULATE)
+#include "cuda_emu.h"      // tests/emu: host stand-in for the CUDA runtime (test infrastructure)
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200conv.h"
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int kDPre = 4;          // max prefetch distance of the CMAC kernels (rows readable past the end)
+constexpr int kPadP = 32;         // H / history rows are padded to a multiple of this
+constexpr int kMaxTT = 32;        // slack rows after the newest X row
+constexpr int kDefaultBatch = 4736;   // 148 SMs * 32
+constexpr int kMaxBlockLog2 = 13;     // B <= 8192 (two M-point ping-pong buffers = 128 KB smem)
+
+inline size_t next_pow2(size_t v) { size_t p = 1; while (p < v) p *= 2; return p; }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Stage {
+  int B = 0;
+  size_t tap_off = 0;      // first IR tap of this stage
+  size_t tap_end = 0;      // one past the last tap (over all channels)
+  int q = 0;               // output delay in blocks (tap_off / B)
+  int P_full = 0;          // partitions of the stage (max over channels)
+  int p_begin = 0, p_end = 0;   // this shard's partition range
+  int P = 0;               // p_end - p_begin
+  int Prows = 0;           // allocated H rows
+  int hist = 0;            // X rows kept before the open block
+  int Tcap = 0;            // max blocks per launch group
+  int R = 0;               // X rows allocated
+  long long head = 0;      // X row of the open block
+  long long blocks_done = 0;   // completed blocks since init/clear
+  int fill = 0;            // samples of the open block already buffered
+  float2* H = nullptr;
+  float2* X = nullptr;
+  float2* Y = nullptr;
+  float2* tw = nullptr;
+  float* inbuf = nullptr;
+  size_t in_stride = 0;
+  float* fut = nullptr;
+  size_t ring = 0;
+};
+
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+}  // namespace
+
+struct b200conv {
+  b200conv_config cfg{};
+  int C = 1;
+  std::string err;
+  bool sticky_cuda_error = false;
+  std::vector<Stage> stages;
+  std::vector<size_t> ir_len;     // post-trim
+  size_t Lmax = 0;                // max samples per launch group
+  long long abs_pos = 0;          // absolute stream position (samples since init/clear)
+  cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{};
+  float* din[2] = {nullptr, nullptr};
+  float* dout[2] = {nullptr, nullptr};
+  unsigned long long launches = 0;
+  // timing
+  bool timing = false;
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+  float t_cmac = 0, t_fft = 0, t_ifft = 0;
+  int n_cmac = 0;
+  // sharding
+  b200conv_reduce_fn reduce = nullptr;
+  void* reduce_user = nullptr;
+  int smem_optin = 0;
+};
+
+namespace {
+
+#define CU_CHECK(h, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      (h)->sticky_cuda_error = true;                                                       \
+      return B200CONV_ECUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+int fail(b200conv* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+void free_stage(Stage& s) {
+  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y); cudaFree(s.tw); cudaFree(s.inbuf); cudaFree(s.fut);
+  s = Stage();
+}
+
+void free_all(b200conv* h) {
+  for (auto& s : h->stages) free_stage(s);
+  h->stages.clear();
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->din[i]); cudaFree(h->dout[i]);
+    h->din[i] = h->dout[i] = nullptr;
+  }
+  h->ir_len.assign(h->C, 0);
+  h->abs_pos = 0;
+  h->Lmax = 0;
+}
+
+// ---- timing helpers ------------------------------------------------------------------------
+enum { kKindFft = 0, kKindCmac = 1, kKindIfft = 2 };
+
+int timing_begin(b200conv* h, int kind) {
+  if (!h->timing) return -1;
+  if (h->ev_used == h->ev_pool.size()) {
+    EventPair p;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
+    h->ev_pool.push_back(p);
+  }
+  int id = (int)h->ev_used++;
+  h->ev_pool[id].kind = kind;
+  cudaEventRecord(h->ev_pool[id].a, h->s_main);
+  return id;
+}
+void timing_end(b200conv* h, int id) {
+  if (id >= 0) cudaEventRecord(h->ev_pool[id].b, h->s_main);
+}
+void timing_collect(b200conv* h) {
+  h->t_cmac = h->t_fft = h->t_ifft = 0;
+  h->n_cmac = 0;
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b) != cudaSuccess) continue;
+    if (h->ev_pool[i].kind == kKindCmac) { h->t_cmac += ms; h->n_cmac++; }
+    else if (h->ev_pool[i].kind == kKindFft) h->t_fft += ms;
+    else h->t_ifft += ms;
+  }
+}
+
+// ---- kernel launchers ----------------------------------------------------------------------
+void fft_geometry(int M, int nblocks, dim3* grid_xy, dim3* block, size_t* smem) {
+  int tx = std::max(1, std::min(256, M / 4));
+  int ty = std::max(1, 128 / tx);
+  ty = std::min(ty, std::max(1, nblocks));
+  *block = dim3(tx, ty, 1);
+  grid_xy->x = (nblocks + ty - 1) / ty;
+  *smem = (size_t)ty * 2 * M * sizeof(float2);
+}
+
+int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
+  dim3 grid, block; size_t smem;
+  fft_geometry(P.M, P.nblocks, &grid, &block, &smem);
+  grid.y = C; grid.z = 1;
+  int id = timing_begin(h, kKindFft);
+#if defined(PC_EMULATE)
+  pc::emu_fwd_fft({(int)grid.x, (int)grid.y, 1}, {(int)block.x, (int)block.y, 1}, P);
+#else
+  pc::k_fwd_fft<<<grid, block, smem, h->s_main>>>(P);
+#endif
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+int launch_inv(b200conv* h, const pc::InvParams& P, int C) {
+  dim3 grid, block; size_t smem;
+  fft_geometry(P.M, P.nblocks, &grid, &block, &smem);
+  grid.y = C; grid.z = 1;
+  int id = timing_begin(h, kKindIfft);
+#if defined(PC_EMULATE)
+  pc::emu_inv_fft_ola({(int)grid.x, (int)grid.y, 1}, {(int)block.x, (int)block.y, 1}, P);
+#else
+  pc::k_inv_fft_ola<<<grid, block, smem, h->s_main>>>(P);
+#endif
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+template <int TT, int D, int TW>
+void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
+  P.Ppad = round_up(P.Ppad, TT);
+  dim3 block(32, TW, 1);
+  dim3 grid((P.B + 31) / 32, (P.nblocks + TT * TW - 1) / (TT * TW), C);
+#if defined(PC_EMULATE)
+  (void)block;
+  pc::emu_cmac_batch<TT, D, TW>({(int)grid.x, (int)grid.y, (int)grid.z}, P);
+#else
+  pc::k_cmac_batch<TT, D, TW><<<grid, block, 0, h->s_main>>>(P);
+#endif
+}
+
+// P.Ppad enters as the number of real (unpadded) partition rows of this shard
+int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
+  int variant = h->cfg.cmac_variant;
+  if (variant == 0) variant = (P.nblocks >= 64) ? 1 : 3;
+  int id = timing_begin(h, kKindCmac);
+  switch (variant) {
+    case 1: launch_cmac_t<16, 4, 8>(h, P, C); break;
+    case 2: launch_cmac_t<16, 4, 4>(h, P, C); break;
+    case 3: launch_cmac_t<8, 4, 4>(h, P, C); break;
+    case 4: launch_cmac_t<8, 4, 8>(h, P, C); break;
+    case 5: launch_cmac_t<16, 2, 8>(h, P, C); break;
+    case 6: launch_cmac_t<32, 4, 4>(h, P, C); break;
+    case 7: launch_cmac_t<4, 4, 8>(h, P, C); break;
+    default: return fail(h, B200CONV_EINVAL, "unknown cmac_variant");
+  }
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
+int set_device(b200conv* h) {
+  CU_CHECK(h, cudaSetDevice(h->cfg.device));
+  return 0;
+}
+
+// ---- IR load -------------------------------------------------------------------------------
+size_t trimmed_len(const float* ir, size_t n) {
+  // FFTConvolver.cpp:103-106 / TwoStageFFTConvolver.cpp:107-110: absolute 1e-6 threshold
+  while (n > 0 && std::fabs(ir[n - 1]) < 0.000001f) --n;
+  return n;
+}
+
+int build_stage(b200conv* h, Stage& s, const float* const* ir, const std::vector<size_t>& L) {
+  const int C = h->C;
+  const int B = s.B;
+  // partitions of this stage (max over channels)
+  size_t maxlen = 0;
+  std::vector<int> len_c(C, 0);
+  for (int c = 0; c < C; ++c) {
+    size_t e = std::min(L[c], s.tap_end);
+    size_t n = e > s.tap_off ? e - s.tap_off : 0;
+    len_c[c] = (int)n;
+    maxlen = std::max(maxlen, n);
+  }
+  s.P_full = (int)((maxlen + B - 1) / B);
+  s.q = (int)(s.tap_off / B);
+  // shard range
+  const int G = std::max(1, h->cfg.shard_count), g = h->cfg.shard_rank;
+  const int per = (s.P_full + G - 1) / G;
+  s.p_begin = std::min(s.P_full, g * per);
+  s.p_end = std::min(s.P_full, (g + 1) * per);
+  s.P = s.p_end - s.p_begin;
+  s.Prows = round_up(std::max(s.P, 1), kPadP) + kDPre;
+  s.hist = s.p_begin + round_up(std::max(s.P, 1), kPadP) + kDPre;
+
+  // twiddles exp(-2*pi*i*j/N), N = 2B, computed in double
+  const int N = 2 * B;
+  std::vector<float2> tw(N);
+  for (int j = 0; j < N; ++j) {
+    const double a = -2.0 * M_PI * (double)j / (double)N;
+    tw[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  CU_CHECK(h, cudaMalloc(&s.tw, N * sizeof(float2)));
+  CU_CHECK(h, cudaMemcpyAsync(s.tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice, h->s_main));
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+
+  // H: upload this shard's taps, transform
+  const size_t hrow = (size_t)B;
+  CU_CHECK(h, cudaMalloc(&s.H, (size_t)C * s.Prows * hrow * sizeof(float2)));
+  CU_CHECK(h, cudaMemsetAsync(s.H, 0, (size_t)C * s.Prows * hrow * sizeof(float2), h->s_main));
+  if (s.P > 0) {
+    const size_t taps_per_c = (size_t)s.P * B;
+    std::vector<float> host((size_t)C * taps_per_c, 0.0f);
+    std::vector<int> nvalid(C, 0);
+    for (int c = 0; c < C; ++c) {
+      const long long first = (long long)s.p_begin * B;            // within the stage
+      long long n = (long long)len_c[c] - first;
+      n = std::max(0LL, std::min(n, (long long)taps_per_c));
+      nvalid[c] = (int)n;
+      if (n > 0) std::memcpy(&host[(size_t)c * taps_per_c], ir[c] + s.tap_off + first, (size_t)n * sizeof(float));
+    }
+    float* dtaps = nullptr; int* dnv = nullptr;
+    CU_CHECK(h, cudaMalloc(&dtaps, host.size() * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&dnv, C * sizeof(int)));
+    CU_CHECK(h, cudaMemcpyAsync(dtaps, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    CU_CHECK(h, cudaMemcpyAsync(dnv, nvalid.data(), C * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
+    pc::FwdParams fp{};
+    fp.src = dtaps; fp.src_cstride = (long long)taps_per_c;
+    fp.nvalid_c = dnv; fp.nvalid = 0;
+    fp.dst = s.H; fp.dst_cstride = (long long)s.Prows * B; fp.dst_row0 = 0;
+    fp.tw = s.tw; fp.M = B; fp.nblocks = s.P;
+    int rc = launch_fwd(h, fp, C);
+    if (rc) { cudaFree(dtaps); cudaFree(dnv); return rc; }
+    CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    cudaFree(dtaps); cudaFree(dnv);
+  }
+  return 0;
+}
+
+int alloc_stage_state(b200conv* h, Stage& s) {
+  const int C = h->C, B = s.B;
+  s.Tcap = (int)(h->Lmax / B) + 2;
+  s.R = 2 * s.hist + s.Tcap + kMaxTT;
+  CU_CHECK(h, cudaMalloc(&s.X, (size_t)C * s.R * B * sizeof(float2)));
+  CU_CHECK(h, cudaMalloc(&s.Y, (size_t)(1 + s.Tcap) * C * B * sizeof(float2)));
+  s.in_stride = (size_t)B + h->Lmax;
+  CU_CHECK(h, cudaMalloc(&s.inbuf, (size_t)C * s.in_stride * sizeof(float)));
+  if (s.q > 0) {
+    s.ring = next_pow2((size_t)(s.q + 2) * B + h->Lmax + B);
+    CU_CHECK(h, cudaMalloc(&s.fut, (size_t)C * s.ring * sizeof(float)));
+  }
+  return 0;
+}
+
+int clear_state(b200conv* h) {
+  for (auto& s : h->stages) {
+    const int C = h->C, B = s.B;
+    CU_CHECK(h, cudaMemsetAsync(s.X, 0, (size_t)C * s.R * B * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(s.Y, 0, (size_t)(1 + s.Tcap) * C * B * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(s.inbuf, 0, (size_t)C * s.in_stride * sizeof(float), h->s_main));
+    if (s.fut) CU_CHECK(h, cudaMemsetAsync(s.fut, 0, (size_t)C * s.ring * sizeof(float), h->s_main));
+    s.head = s.hist;
+    s.blocks_done = 0;
+    s.fill = 0;
+  }
+  h->abs_pos = 0;
+  return 0;
+}
+
+int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* offsets,
+                const float* const* ir, const size_t* ir_len) {
+  if (int rc = set_device(h)) return rc;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  free_all(h);
+  const int C = h->C;
+  for (int s = 0; s < n_stages; ++s)
+    if (blocks[s] == 0) return fail(h, B200CONV_EINVAL, "block size 0");
+  std::vector<size_t> L(C);
+  size_t Lir = 0;
+  for (int c = 0; c < C; ++c) {
+    L[c] = (ir && ir[c] && ir_len) ? trimmed_len(ir[c], ir_len[c]) : 0;
+    Lir = std::max(Lir, L[c]);
+  }
+  h->ir_len = L;
+  if (Lir == 0) return B200CONV_OK;      // empty IR: legal, process() writes zeros (FFTConvolver.cpp:108-111)
+
+  std::vector<Stage> st;
+  for (int s = 0; s < n_stages; ++s) {
+    Stage x;
+    const size_t b = next_pow2(blocks[s]);                    // FFTConvolver.cpp:113
+    if (b > (size_t(1) << kMaxBlockLog2)) return fail(h, B200CONV_EINVAL, "block size > 8192 not supported");
+    x.B = (int)b;
+    x.tap_off = offsets ? offsets[s] : 0;
+    x.tap_end = (s + 1 < n_stages) ? offsets[s + 1] : Lir;
+    if (x.tap_off >= Lir) break;                              // IR shorter than this stage's offset
+    x.tap_end = std::min(x.tap_end, Lir);
+    if (s > 0 && (x.tap_off % b != 0 || x.tap_off < b))
+      return fail(h, B200CONV_EINVAL, "stage offset must be a multiple of (and >=) its block size");
+    st.push_back(x);
+  }
+  const int B0 = st[0].B;
+  int batch = h->cfg.max_batch_blocks > 0 ? h->cfg.max_batch_blocks : kDefaultBatch;
+  h->Lmax = (size_t)batch * B0;
+  for (auto& x : st) h->Lmax = std::max(h->Lmax, (size_t)2 * x.B);
+  h->stages = st;
+  for (auto& s : h->stages) {
+    if (int rc = build_stage(h, s, ir, L)) { free_all(h); return rc; }
+    if (int rc = alloc_stage_state(h, s)) { free_all(h); return rc; }
+  }
+  for (int i = 0; i < 2; ++i) {
+    CU_CHECK(h, cudaMalloc(&h->din[i], (size_t)C * h->Lmax * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&h->dout[i], (size_t)C * h->Lmax * sizeof(float)));
+  }
+  if (int rc = clear_state(h)) { free_all(h); return rc; }
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  return B200CONV_OK;
+}
+
+// ---- one launch group: n <= Lmax samples, device-resident ------------------------------------
+int compact_timeline(b200conv* h, Stage& s) {
+  const int C = h->C, B = s.B;
+  const size_t bytes = (size_t)s.hist * B * sizeof(float2);
+  for (int c = 0; c < C; ++c) {
+    float2* base = s.X + (size_t)c * s.R * B;
+    CU_CHECK(h, cudaMemcpyAsync(base, base + (size_t)(s.head - s.hist) * B, bytes, cudaMemcpyDeviceToDevice, h->s_main));
+  }
+  s.head = s.hist;
+  return 0;
+}
+
+int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n) {
+  const int C = h->C;
+  const bool root = h->cfg.shard_rank == 0;
+  // stages >= 1 first (their look-ahead output may be consumed by the head within this group)
+  for (int si = (int)h->stages.size() - 1; si >= 0; --si) {
+    Stage& s = h->stages[si];
+    const int B = s.B;
+    // append the new samples behind the open block's samples
+    CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                  n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+    const size_t total = (size_t)s.fill + n;
+    const int complete = (int)(total / B);
+    const int partial = (int)(total % B);
+    const int nb = (si == 0) ? complete + (partial > 0 ? 1 : 0) : complete;
+    if (nb > 0) {
+      if (s.head + nb + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
+      pc::FwdParams fp{};
+      fp.src = s.inbuf; fp.src_cstride = (long long)s.in_stride; fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
+      fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
+      fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+      if (int rc = launch_fwd(h, fp, C)) return rc;
+
+      pc::CmacParams cp{};
+      cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
+      cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
+      cp.Y = s.Y; cp.y_cstride = B; cp.y_rstride = (long long)C * B; cp.yrow0 = 1;
+      cp.B = B; cp.Ppad = s.P; cp.nblocks = nb;
+      if (int rc = launch_cmac(h, cp, C)) return rc;
+
+      if (h->cfg.shard_count > 1) {
+        if (!h->reduce) return fail(h, B200CONV_ESTATE, "sharded handle without a reduce hook");
+        if (h->reduce(h->reduce_user, reinterpret_cast<float*>(s.Y + (size_t)C * B), (size_t)nb * C * B * 2, h->s_main) != 0)
+          return fail(h, B200CONV_ECUDA, "reduce hook failed");
+      }
+      if (root) {
+        pc::InvParams ip{};
+        ip.Y = s.Y; ip.y_cstride = B; ip.y_rstride = (long long)C * B; ip.yrow0 = 1;
+        ip.tw = s.tw; ip.M = B; ip.nblocks = nb; ip.scale = 1.0f / (float)B;
+        if (si == 0) {
+          ip.dst = out_dev; ip.dst_cstride = (long long)out_stride;
+          ip.index0 = -(long long)s.fill; ip.lo = 0; ip.hi = (long long)n; ip.mask = -1;
+          ip.abs0 = h->abs_pos - s.fill;
+          int na = 0;
+          for (size_t sj = 1; sj < h->stages.size() && na < 3; ++sj) {
+            ip.add[na] = h->stages[sj].fut; ip.add_cstride[na] = (long long)h->stages[sj].ring;
+            ip.add_mask[na] = (long long)h->stages[sj].ring - 1;
+            ++na;
+          }
+          ip.n_add = na;
+        } else {
+          ip.dst = s.fut; ip.dst_cstride = (long long)s.ring;
+          ip.index0 = (s.blocks_done + s.q) * (long long)B;
+          ip.lo = 0; ip.hi = (long long)1 << 62; ip.mask = (long long)s.ring - 1;
+          ip.n_add = 0; ip.abs0 = 0;
+        }
+        if (int rc = launch_inv(h, ip, C)) return rc;
+      }
+    }
+    // state update
+    if (complete > 0) {
+      CU_CHECK(h, cudaMemcpyAsync(s.Y, s.Y + (size_t)complete * C * B, (size_t)C * B * sizeof(float2),
+                                  cudaMemcpyDeviceToDevice, h->s_main));
+      if (partial > 0)
+        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), s.inbuf + (size_t)complete * B,
+                                      s.in_stride * sizeof(float), partial * sizeof(float), C,
+                                      cudaMemcpyDeviceToDevice, h->s_main));
+      s.head += complete;
+      s.blocks_done += complete;
+    }
+    s.fill = partial;
+  }
+  h->abs_pos += (long long)n;
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* b200conv_version(void) {
+#if defined(PC_EMULATE)
+  return "b200conv 0.1 EMULATED-ON-CPU (tests only)";
+#else
+  return "b200conv 0.1 (sm_100a, hand-written Stockham FFT + register-tiled FDL sweep)";
+#endif
+}
+
+b200conv_t* b200conv_create(const b200conv_config* cfg) {
+  if (!cfg || cfg->n_channels < 1) return nullptr;
+  b200conv* h = new (std::nothrow) b200conv();
+  if (!h) return nullptr;
+  h->cfg = *cfg;
+  if (h->cfg.shard_count < 1) h->cfg.shard_count = 1;
+  if (h->cfg.shard_rank < 0 || h->cfg.shard_rank >= h->cfg.shard_count) h->cfg.shard_rank = 0;
+  h->C = cfg->n_channels;
+  h->ir_len.assign(h->C, 0);
+  // CUDA resources; failures are recorded and reported by the first real call
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) {
+    h->err = "cudaSetDevice failed: no usable CUDA device";
+    h->sticky_cuda_error = true;
+    cudaGetLastError();
+    return h;
+  }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = ok && cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+#if !defined(PC_EMULATE)
+  if (ok) {
+    // the FFT kernels need up to 128 KB of dynamic shared memory (B = 8192)
+    ok = cudaFuncSetAttribute(pc::k_fwd_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+  }
+#endif
+  if (!ok) {
+    h->err = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
+    h->sticky_cuda_error = true;
+  }
+  return h;
+}
+
+void b200conv_destroy(b200conv_t* h) {
+  if (!h) return;
+  if (!h->sticky_cuda_error || h->s_main) {
+    cudaSetDevice(h->cfg.device);
+    if (h->s_main) cudaStreamSynchronize(h->s_main);
+    free_all(h);
+    for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (int i = 0; i < 2; ++i) {
+      if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+      if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+      if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+  }
+  delete h;
+}
+
+const char* b200conv_last_error(const b200conv_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+#define REQUIRE_CUDA(h)                                                   \
+  do {                                                                    \
+    if (!(h)) return B200CONV_EINVAL;                                     \
+    if ((h)->sticky_cuda_error) return B200CONV_ECUDA;                    \
+  } while (0)
+
+int b200conv_init_uniform(b200conv_t* h, size_t block, const float* const* ir, const size_t* ir_len) {
+  REQUIRE_CUDA(h);
+  const size_t off = 0;
+  return init_common(h, 1, &block, &off, ir, ir_len);
+}
+
+int b200conv_init_twostage(b200conv_t* h, size_t head_block, size_t tail_block,
+                           const float* const* ir, const size_t* ir_len) {
+  REQUIRE_CUDA(h);
+  if (head_block == 0 || tail_block == 0) {                       // TwoStageFFTConvolver.cpp:94-97
+    if (int rc = set_device(h)) return rc;
+    cudaStreamSynchronize(h->s_main);
+    free_all(h);
+    return fail(h, B200CONV_EINVAL, "block size 0");
+  }
+  if (head_block > tail_block) std::swap(head_block, tail_block);  // :100-104
+  const size_t hb = next_pow2(head_block), tb = next_pow2(tail_block);   // :117-118
+  // head covers taps [0, T), tail0 (same block size as the head, :123-129) taps [T, 2T): the two
+  // are one uniform stage of block hb over [0, 2T); the tail runs block T over [2T, L) (:131-138).
+  const size_t blocks[2] = {hb, tb};
+  const size_t offsets[2] = {0, 2 * tb};
+  return init_common(h, 2, blocks, offsets, ir, ir_len);
+}
+
+int b200conv_init_stages(b200conv_t* h, int n_stages, const size_t* blocks, const size_t* offsets,
+                         const float* const* ir, const size_t* ir_len) {
+  REQUIRE_CUDA(h);
+  if (n_stages < 1 || n_stages > 4 || !blocks || !offsets || offsets[0] != 0)
+    return fail(h, B200CONV_EINVAL, "need 1..4 stages with offsets[0] == 0");
+  return init_common(h, n_stages, blocks, offsets, ir, ir_len);
+}
+
+int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride,
+                            float* out_dev, size_t out_stride, size_t len, int sync) {
+  REQUIRE_CUDA(h);
+  if (int rc = set_device(h)) return rc;
+  if (h->timing) h->ev_used = 0;
+  if (h->stages.empty()) {      // no IR: zeros (FFTConvolver.cpp:157-161)
+    if (len) CU_CHECK(h, cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, len * sizeof(float), h->C, h->s_main));
+  } else {
+    const size_t B0 = h->stages[0].B;
+    size_t done = 0;
+    while (done < len) {
+      // keep fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
+      size_t n = std::min(len - done, h->Lmax - B0);
+      if (int rc = run_group(h, in_dev + done, in_stride, out_dev + done, out_stride, n)) return rc;
+      done += n;
+    }
+  }
+  if (sync || h->timing) {
+    CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    if (h->timing) timing_collect(h);
+  }
+  return B200CONV_OK;
+}
+
+int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, size_t len) {
+  REQUIRE_CUDA(h);
+  if (len == 0) return B200CONV_OK;
+  if (!in || !out) return fail(h, B200CONV_EINVAL, "null buffer");
+  if (int rc = set_device(h)) return rc;
+  const int C = h->C;
+  if (h->stages.empty()) {
+    for (int c = 0; c < C; ++c) std::memset(out[c], 0, len * sizeof(float));
+    return B200CONV_OK;
+  }
+  const size_t B0 = h->stages[0].B;
+  const size_t chunk = h->Lmax - B0;
+  if (len <= chunk) {
+    // latency path: one stream, one group
+    for (int c = 0; c < C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len)) return rc;
+    for (int c = 0; c < C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    return B200CONV_OK;
+  }
+  // throughput path: H2D / compute / D2H of successive groups overlap on three streams
+  size_t done = 0;
+  int i = 0;
+  // split long calls into at least 4 groups so that the copies overlap with compute
+  size_t grp = std::min(chunk, std::max((size_t)B0 * 64, (len / 4 + B0 - 1) / B0 * B0));
+  for (; done < len; ++i) {
+    const int b = i & 1;
+    const size_t n = std::min(len - done, grp);
+    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));     // din[b] free again
+    for (int c = 0; c < C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * h->Lmax, in[c] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+    CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
+    CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_h2d[b], 0));
+    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_d2h[b], 0));    // dout[b] drained
+    if (int rc = run_group(h, h->din[b], h->Lmax, h->dout[b], h->Lmax, n)) return rc;
+    CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_main));
+    CU_CHECK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+    for (int c = 0; c < C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(out[c] + done, h->dout[b] + (size_t)c * h->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    CU_CHECK(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
+    done += n;
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->s_out));
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  return B200CONV_OK;
+}
+
+int b200conv_clear(b200conv_t* h) {
+  REQUIRE_CUDA(h);
+  if (int rc = set_device(h)) return rc;
+  if (int rc = clear_state(h)) return rc;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  return B200CONV_OK;
+}
+
+int b200conv_reset(b200conv_t* h) {
+  REQUIRE_CUDA(h);
+  if (int rc = set_device(h)) return rc;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  free_all(h);
+  return B200CONV_OK;
+}
+
+int b200conv_num_stages(const b200conv_t* h) { return h ? (int)h->stages.size() : 0; }
+
+int b200conv_stage(const b200conv_t* h, int s, b200conv_stage_info* out) {
+  if (!h || !out || s < 0 || s >= (int)h->stages.size()) return B200CONV_EINVAL;
+  const Stage& st = h->stages[s];
+  out->block = st.B; out->partitions = st.P_full; out->tap_offset = st.tap_off;
+  out->p_begin = st.p_begin; out->p_end = st.p_end;
+  return B200CONV_OK;
+}
+
+size_t b200conv_ir_len(const b200conv_t* h, int channel) {
+  if (!h || channel < 0 || channel >= h->C) return 0;
+  return h->ir_len[channel];
+}
+
+unsigned long long b200conv_launch_count(const b200conv_t* h) { return h ? h->launches : 0; }
+
+int b200conv_set_timing(b200conv_t* h, int enable) {
+  if (!h) return B200CONV_EINVAL;
+  h->timing = enable != 0;
+  return B200CONV_OK;
+}
+
+int b200conv_last_timing(const b200conv_t* h, float* cmac_ms, float* fft_ms, float* ifft_ms, int* cmac_launches) {
+  if (!h) return B200CONV_EINVAL;
+  if (cmac_ms) *cmac_ms = h->t_cmac;
+  if (fft_ms) *fft_ms = h->t_fft;
+  if (ifft_ms) *ifft_ms = h->t_ifft;
+  if (cmac_launches) *cmac_launches = h->n_cmac;
+  return B200CONV_OK;
+}
+
+void* b200conv_stream(const b200conv_t* h) { return h ? (void*)h->s_main : nullptr; }
+
+int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user) {
+  if (!h) return B200CONV_EINVAL;
+  h->reduce = fn; h->reduce_user = user;
+  return B200CONV_OK;
+}
+
+void* b200conv_alloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void b200conv_free_host(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

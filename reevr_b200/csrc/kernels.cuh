@@ -1,0 +1,480 @@
+// kernels.cuh — sm_100a kernels of the partitioned-convolution hot path.
+//
+//   K1 k_fwd_fft      X[t]  = RFFT_2B([x_t ; 0_B])        replaces CopyAndPad + AudioFFT::fft
+//                                                         (FFTConvolver.cpp:172-173, AudioFFT.cpp:114-137);
+//                                                         the same kernel builds the IR spectra H[p]
+//                                                         (FFTConvolver::init, FFTConvolver.cpp:129-137)
+//   K2 k_cmac_batch   Y[t]  = sum_p H[p] (.) X[t-p]       replaces the ComplexMultiplyAccumulate sweep over
+//                                                         the frequency-domain delay line
+//                                                         (FFTConvolver.cpp:176-187, Utilities.cpp:62-111)
+//   K3 k_inv_fft_ola  y_t   = IRFFT_2B(Y[t] + (-1)^k Y[t-1])[0:B] (+ look-ahead stage outputs)
+//                                                         replaces AudioFFT::ifft + Sum + overlap save
+//                                                         (FFTConvolver.cpp:190-204, AudioFFT.cpp:139-159,
+//                                                         Utilities.cpp:34-51) and the tail sums of
+//                                                         TwoStageFFTConvolver::process (:166-193)
+//
+// Spectrum layout (private to the engine, as in the reference where spectra never cross the API,
+// FFTConvolver.h:83-96): interleaved float2, exactly B entries per 2B-point real transform;
+// entry 0 packs the two purely real bins as (DC, Nyquist), entries 1..B-1 are bins 1..B-1.
+// Rows are therefore B*8 bytes — a power of two, 32-byte-sector aligned for every B >= 4.
+//
+// The per-thread / per-phase bodies are plain inline functions so that tests/emu (g++) can run
+// the identical index arithmetic on the CPU; the __global__ wrappers only add the thread
+// geometry and the __syncthreads() between phases.
+#pragma once
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define PC_HD __host__ __device__ __forceinline__
+#define PC_D __device__ __forceinline__
+#else
+#include <cmath>
+#define PC_HD inline
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
+
+namespace pc {
+
+// ------------------------------------------------------------------------------------------
+// complex helpers
+// ------------------------------------------------------------------------------------------
+PC_HD float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PC_HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PC_HD float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+PC_HD float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
+
+PC_HD int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// radix of the Stockham pass that starts with sub-transform length p (M total): one radix-2
+// pass first when log2(M/p) is odd, radix-4 otherwise.
+PC_HD int pass_radix(int M, int p) { return (ilog2(M / p) & 1) ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------
+// One Stockham autosort pass, out of place (in -> out), butterfly i in [0, M/R).
+// tw = exp(-2*pi*i*j/(2M)), j < 2M (full circle of the REAL transform size N = 2M).
+// ------------------------------------------------------------------------------------------
+template <bool INV>
+PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, int M, int p, int R, int i) {
+  const int k = i & (p - 1);
+  const int j = (i - k) * R + k;
+  const int stride = M / R;
+  const int tstep = (2 * M) / (p * R);          // table step for exp(-2*pi*i*k/(p*R))
+  if (R == 4) {
+    float2 a0 = in[i];
+    float2 a1 = in[i + stride];
+    float2 a2 = in[i + 2 * stride];
+    float2 a3 = in[i + 3 * stride];
+    if (k != 0) {
+      float2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      a1 = c_mul(a1, w1); a2 = c_mul(a2, w2); a3 = c_mul(a3, w3);
+    }
+    const float2 b0 = c_add(a0, a2), b1 = c_sub(a0, a2), b2 = c_add(a1, a3);
+    const float2 d = c_sub(a1, a3);
+    // forward: -i*d ; inverse: +i*d
+    const float2 b3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    out[j] = c_add(b0, b2);
+    out[j + p] = c_add(b1, b3);
+    out[j + 2 * p] = c_sub(b0, b2);
+    out[j + 3 * p] = c_sub(b1, b3);
+  } else {
+    float2 a0 = in[i];
+    float2 a1 = in[i + stride];
+    if (k != 0) {
+      float2 w1 = tw[k * tstep];
+      if (INV) w1.y = -w1.y;
+      a1 = c_mul(a1, w1);
+    }
+    out[j] = c_add(a0, a1);
+    out[j + p] = c_sub(a0, a1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 phases.  Real transform of size N = 2M computed as an M-point complex transform of
+// z[n] = x[2n] + i*x[2n+1] followed by the even/odd split.
+// ------------------------------------------------------------------------------------------
+// load: src = first sample of this block, nv = valid samples (<= M = B), rest is zero padding
+PC_HD void fwd_load(const float* src, int nv, float2* z, int M, int n) {
+  const int i0 = 2 * n, i1 = 2 * n + 1;
+  z[n] = make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
+}
+
+// split: Z = FFT_M(z) -> packed spectrum row X (B = M entries), k in [0, M/2]
+PC_HD void fwd_split(const float2* Z, float2* X, const float2* tw, int M, int k) {
+  if (k == 0) {
+    const float2 z0 = Z[0];
+    X[0] = make_float2(z0.x + z0.y, z0.x - z0.y);      // (DC, Nyquist)
+    return;
+  }
+  const float2 a = Z[k];
+  const float2 b = c_conj(Z[M - k]);
+  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+  const float2 O = make_float2(D.y, -D.x);              // -i * D
+  const float2 wO = c_mul(tw[k], O);
+  X[k] = c_add(E, wO);
+  X[M - k] = c_conj(c_sub(E, wO));
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 phases.
+// ------------------------------------------------------------------------------------------
+// merge + pre-twist: W = Yt + (-1)^k Yp  (overlap-add done in the frequency domain: the second
+// half of IRFFT(Yp) equals the first half of IRFFT((-1)^k Yp)), then Z such that
+// IFFT_M(Z)[n] = x[2n] + i*x[2n+1].   k in [0, M/2].
+PC_HD float2 ola_merge(const float2* Yt, const float2* Yp, int M, int k) {
+  const float2 a = Yt[k], b = Yp[k];
+  if (k == 0) {
+    const float s = (M & 1) ? -1.0f : 1.0f;             // Nyquist index M: (-1)^M
+    return make_float2(a.x + b.x, a.y + s * b.y);
+  }
+  return (k & 1) ? c_sub(a, b) : c_add(a, b);
+}
+
+PC_HD void inv_pre(const float2* Yt, const float2* Yp, float2* Z, const float2* tw, int M, int k) {
+  if (k == 0) {
+    const float2 w0 = ola_merge(Yt, Yp, M, 0);
+    Z[0] = make_float2(0.5f * (w0.x + w0.y), 0.5f * (w0.x - w0.y));
+    return;
+  }
+  const float2 a = ola_merge(Yt, Yp, M, k);
+  const float2 b = c_conj(ola_merge(Yt, Yp, M, M - k));
+  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+  const float2 O = c_mul(c_conj(tw[k]), D);
+  Z[k] = make_float2(E.x - O.y, E.y + O.x);
+  Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
+}
+
+// where the B output samples of one block go
+struct OutSpec {
+  float* dst;            // channel base
+  long long index0;      // dst index of sample 0 of this block (before masking)
+  long long lo, hi;      // valid dst index range [lo, hi) (head: this call's samples)
+  long long mask;        // index & mask (ring destination) ; -1 = linear
+  // look-ahead stage rings added on top (head stage only)
+  int n_add;
+  const float* add[3];
+  long long add_mask[3];
+  long long abs0;        // absolute stream position of sample 0 (ring read position)
+};
+
+PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int s) {
+  const long long idx = o.index0 + s;
+  if (idx < o.lo || idx >= o.hi) return;
+  const float2 v = z[s >> 1];
+  float r = ((s & 1) ? v.y : v.x) * scale;
+  for (int a = 0; a < o.n_add; ++a) r += o.add[a][(o.abs0 + s) & o.add_mask[a]];
+  o.dst[idx & o.mask] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: per-thread body of the batched FDL sweep.
+//   thread owns bin k and TT consecutive output blocks t0..t0+TT-1 of one channel:
+//     acc[j] = sum_{p=0}^{Ppad-1} H[p][k] * X[xrow0 + t0 + j - p][k]
+//   H rows beyond P are zero; X rows exist (finite values) for every index touched.
+//   The X window slides by one row per partition and lives in registers: per partition the
+//   thread loads one H value and one X value (16 B) and issues 4*TT FFMAs.
+//   D = software prefetch distance (partitions); TT % D == 0; H/X are readable D rows past the end.
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define PC_LD(p) __ldg(p)
+#else
+#define PC_LD(p) (*(p))
+#endif
+
+template <int TT, int D>
+PC_HD void cmac_thread(const float2* __restrict__ Hk,   // &H[c][0][k]
+                       const float2* __restrict__ Xk,   // &X[c][xrow0 + t0][k]  (row of output t0, p = 0)
+                       long long rowstride,             // B (float2 elements per row)
+                       int Ppad, bool packed_bin,
+                       float2* acc) {
+  float2 win[TT];
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    win[j] = PC_LD(Xk + (long long)j * rowstride);
+    acc[j] = make_float2(0.0f, 0.0f);
+  }
+  float2 hq[D], xq[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    hq[d] = PC_LD(Hk + (long long)d * rowstride);
+    xq[d] = PC_LD(Xk - (long long)(d + 1) * rowstride);
+  }
+  const float2* hp = Hk + (long long)D * rowstride;       // next H row to prefetch
+  const float2* xp = Xk - (long long)(D + 1) * rowstride; // next X row to prefetch
+  for (int p0 = 0; p0 < Ppad; p0 += TT) {
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+      const float2 h = hq[u % D];
+      const float2 xn = xq[u % D];
+      hq[u % D] = PC_LD(hp);
+      xq[u % D] = PC_LD(xp);
+      hp += rowstride;
+      xp -= rowstride;
+      // logical window entry j lives in win[(j - u) mod TT]
+      if (!packed_bin) {
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+          const float2 x = win[(j - u + TT) % TT];
+          acc[j].x = fmaf(h.x, x.x, acc[j].x);
+          acc[j].x = fmaf(-h.y, x.y, acc[j].x);
+          acc[j].y = fmaf(h.x, x.y, acc[j].y);
+          acc[j].y = fmaf(h.y, x.x, acc[j].y);
+        }
+      } else {   // entry 0: two independent real bins (DC, Nyquist)
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+          const float2 x = win[(j - u + TT) % TT];
+          acc[j].x = fmaf(h.x, x.x, acc[j].x);
+          acc[j].y = fmaf(h.y, x.y, acc[j].y);
+        }
+      }
+      // slide: logical j of the next step is logical j-1 now; new logical 0 replaces old TT-1
+      win[(TT - 1 - u + TT) % TT] = xn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch parameter blocks (shared by the CUDA kernels and the CPU emulation drivers)
+// ------------------------------------------------------------------------------------------
+struct FwdParams {
+  const float* src;          // time-domain samples, channel c at src + c*src_cstride
+  long long src_cstride;
+  const int* nvalid_c;       // optional per-channel valid sample count (IR build), else nvalid
+  long long nvalid;          // samples available from src (blocks past it read zeros)
+  float2* dst;               // spectra, channel c at dst + c*dst_cstride, row r at + r*M
+  long long dst_cstride;
+  long long dst_row0;        // row of block 0
+  const float2* tw;
+  int M;                     // = B
+  int nblocks;
+};
+
+struct CmacParams {
+  const float2* H;           // [C][Prows][B]
+  long long h_cstride;
+  const float2* X;           // [C][R][B]
+  long long x_cstride;
+  long long xrow0;           // X row of output block 0 at partition 0
+  float2* Y;                 // output block t of channel c -> Y + c*y_cstride + (yrow0+t)*y_rstride
+  long long y_cstride;
+  long long y_rstride;
+  long long yrow0;
+  int B;
+  int Ppad;                  // multiple of TT
+  int nblocks;
+};
+
+struct InvParams {
+  const float2* Y;           // block t of channel c: Y + c*y_cstride + (yrow0+t)*y_rstride; previous = one row before
+  long long y_cstride;
+  long long y_rstride;
+  long long yrow0;
+  const float2* tw;
+  int M;
+  int nblocks;
+  float scale;               // 1/M
+  // output
+  float* dst; long long dst_cstride;
+  long long index0;          // dst index of sample 0 of block 0
+  long long lo, hi, mask;
+  int n_add;
+  const float* add[3]; long long add_cstride[3]; long long add_mask[3];
+  long long abs0;            // absolute stream position of sample 0 of block 0
+};
+
+#if defined(__CUDACC__)
+// ==========================================================================================
+// __global__ wrappers
+// ==========================================================================================
+
+
+// grid (ceil(nblocks/ty), C), block (tx, ty); dynamic smem = ty * 2 * M * sizeof(float2)
+__global__ void k_fwd_fft(FwdParams P) {
+  extern __shared__ float2 pc_smem[];
+  const int M = P.M;
+  const int tx = threadIdx.x, nth = blockDim.x;
+  const int blk = blockIdx.x * blockDim.y + threadIdx.y;
+  const int c = blockIdx.y;
+  const bool active = blk < P.nblocks;
+  float2* bufA = pc_smem + (size_t)threadIdx.y * 2 * M;
+  float2* bufB = bufA + M;
+  if (active) {
+    const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
+    long long rem = nv_total - (long long)blk * M;
+    const int nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
+    const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
+    for (int n = tx; n < M; n += nth) fwd_load(src, nv, bufA, M, n);
+  }
+  __syncthreads();
+  float2* in = bufA; float2* out = bufB;
+  for (int p = 1; p < M;) {
+    const int R = pass_radix(M, p);
+    if (active)
+      for (int i = tx; i < M / R; i += nth) stockham_butterfly<false>(in, out, P.tw, M, p, R, i);
+    __syncthreads();
+    float2* t = in; in = out; out = t;
+    p *= R;
+  }
+  if (active) {
+    float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
+    for (int k = tx; k <= M / 2; k += nth) fwd_split(in, X, P.tw, M, k);
+  }
+}
+
+
+// grid (ceil(B/32), ceil(nblocks/(TT*TW)), C), block (32, TW)
+template <int TT, int D, int TW>
+__global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = (blockIdx.y * TW + threadIdx.y) * TT;
+  const int c = blockIdx.z;
+  if (k >= P.B || t0 >= P.nblocks) return;
+  const float2* Hk = P.H + (long long)c * P.h_cstride + k;
+  const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
+  float2 acc[TT];
+  if (k == 0) cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, true, acc);
+  else        cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, false, acc);
+  float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
+#pragma unroll
+  for (int j = 0; j < TT; ++j)
+    if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
+}
+
+
+// grid (ceil(nblocks/ty), C), block (tx, ty); dynamic smem = ty * 2 * M * sizeof(float2)
+__global__ void k_inv_fft_ola(InvParams P) {
+  extern __shared__ float2 pc_smem[];
+  const int M = P.M;
+  const int tx = threadIdx.x, nth = blockDim.x;
+  const int blk = blockIdx.x * blockDim.y + threadIdx.y;
+  const int c = blockIdx.y;
+  const bool active = blk < P.nblocks;
+  float2* bufA = pc_smem + (size_t)threadIdx.y * 2 * M;
+  float2* bufB = bufA + M;
+  if (active) {
+    const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
+    const float2* Yp = Yt - P.y_rstride;
+    for (int k = tx; k <= M / 2; k += nth) inv_pre(Yt, Yp, bufA, P.tw, M, k);
+  }
+  __syncthreads();
+  float2* in = bufA; float2* out = bufB;
+  for (int p = 1; p < M;) {
+    const int R = pass_radix(M, p);
+    if (active)
+      for (int i = tx; i < M / R; i += nth) stockham_butterfly<true>(in, out, P.tw, M, p, R, i);
+    __syncthreads();
+    float2* t = in; in = out; out = t;
+    p *= R;
+  }
+  if (active) {
+    OutSpec o;
+    o.dst = P.dst + (long long)c * P.dst_cstride;
+    o.index0 = P.index0 + (long long)blk * M;
+    o.lo = P.lo; o.hi = P.hi; o.mask = P.mask;
+    o.n_add = P.n_add;
+    for (int a = 0; a < 3; ++a) {
+      o.add[a] = a < P.n_add ? P.add[a] + (long long)c * P.add_cstride[a] : nullptr;
+      o.add_mask[a] = P.add_mask[a];
+    }
+    o.abs0 = P.abs0 + (long long)blk * M;
+    for (int s = tx; s < M; s += nth) inv_store(in, M, P.scale, o, s);
+  }
+}
+#endif  // __CUDACC__
+
+
+#if !defined(__CUDACC__)
+// ==========================================================================================
+// CPU emulation drivers (tests/emu only): same phase functions, the CTA's threads replaced by
+// loops, __syncthreads() by the loop boundaries.  Geometry arguments mirror the launches.
+// ==========================================================================================
+struct EmuDim { int x, y, z; };
+
+inline void emu_fwd_fft(EmuDim grid, EmuDim block, const FwdParams& P) {
+  const int M = P.M;
+  float2* bufA = new float2[(size_t)M];
+  float2* bufB = new float2[(size_t)M];
+  for (int c = 0; c < grid.y; ++c)
+    for (int bx = 0; bx < grid.x; ++bx)
+      for (int ty = 0; ty < block.y; ++ty) {
+        const int blk = bx * block.y + ty;
+        if (blk >= P.nblocks) continue;
+        const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
+        long long rem = nv_total - (long long)blk * M;
+        const int nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
+        const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
+        for (int n = 0; n < M; ++n) fwd_load(src, nv, bufA, M, n);
+        float2* in = bufA; float2* out = bufB;
+        for (int p = 1; p < M;) {
+          const int R = pass_radix(M, p);
+          for (int i = 0; i < M / R; ++i) stockham_butterfly<false>(in, out, P.tw, M, p, R, i);
+          float2* t = in; in = out; out = t;
+          p *= R;
+        }
+        float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
+        for (int k = 0; k <= M / 2; ++k) fwd_split(in, X, P.tw, M, k);
+      }
+  delete[] bufA; delete[] bufB;
+}
+
+template <int TT, int D, int TW>
+inline void emu_cmac_batch(EmuDim grid, const CmacParams& P) {
+  for (int c = 0; c < grid.z; ++c)
+    for (int by = 0; by < grid.y; ++by)
+      for (int bx = 0; bx < grid.x; ++bx)
+        for (int w = 0; w < TW; ++w)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int k = bx * 32 + lane;
+            const int t0 = (by * TW + w) * TT;
+            if (k >= P.B || t0 >= P.nblocks) continue;
+            const float2* Hk = P.H + (long long)c * P.h_cstride + k;
+            const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
+            float2 acc[TT];
+            cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
+            float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
+            for (int j = 0; j < TT; ++j)
+              if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
+          }
+}
+
+inline void emu_inv_fft_ola(EmuDim grid, EmuDim block, const InvParams& P) {
+  const int M = P.M;
+  float2* bufA = new float2[(size_t)M];
+  float2* bufB = new float2[(size_t)M];
+  for (int c = 0; c < grid.y; ++c)
+    for (int bx = 0; bx < grid.x; ++bx)
+      for (int ty = 0; ty < block.y; ++ty) {
+        const int blk = bx * block.y + ty;
+        if (blk >= P.nblocks) continue;
+        const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
+        const float2* Yp = Yt - P.y_rstride;
+        for (int k = 0; k <= M / 2; ++k) inv_pre(Yt, Yp, bufA, P.tw, M, k);
+        float2* in = bufA; float2* out = bufB;
+        for (int p = 1; p < M;) {
+          const int R = pass_radix(M, p);
+          for (int i = 0; i < M / R; ++i) stockham_butterfly<true>(in, out, P.tw, M, p, R, i);
+          float2* t = in; in = out; out = t;
+          p *= R;
+        }
+        OutSpec o;
+        o.dst = P.dst + (long long)c * P.dst_cstride;
+        o.index0 = P.index0 + (long long)blk * M;
+        o.lo = P.lo; o.hi = P.hi; o.mask = P.mask;
+        o.n_add = P.n_add;
+        for (int a = 0; a < 3; ++a) {
+          o.add[a] = a < P.n_add ? P.add[a] + (long long)c * P.add_cstride[a] : nullptr;
+          o.add_mask[a] = P.add_mask[a];
+        }
+        o.abs0 = P.abs0 + (long long)blk * M;
+        for (int sidx = 0; sidx < M; ++sidx) inv_store(in, M, P.scale, o, sidx);
+      }
+  delete[] bufA; delete[] bufB;
+}
+#endif  // !__CUDACC__
+
+}  // namespace pc

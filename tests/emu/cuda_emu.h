@@ -1,0 +1,58 @@
+// cuda_emu.h — TEST INFRASTRUCTURE ONLY.
+// Minimal host stand-in for the CUDA runtime calls engine.cu makes, so that the engine's host
+// logic (stage scheduling, timeline compaction, staging, look-ahead rings) and the kernels'
+// index arithmetic can be exercised by the CPU test-suite in a container without a GPU.
+// "Device" memory is host memory; every operation is synchronous.  Built only into
+// tests/emu/libb200conv_emu.so; the product library is always compiled by nvcc without it.
+#pragma once
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+typedef void* cudaStream_t;
+struct EmuEvent { std::chrono::steady_clock::time_point t; };
+typedef EmuEvent* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (void*)1; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)1; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
+  *p = (T*)std::malloc(n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memmove(d, s, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemset2DAsync(void* d, size_t dp, int v, size_t w, size_t h, cudaStream_t) {
+  for (size_t r = 0; r < h; ++r) std::memset((char*)d + r * dp, v, w);
+  return cudaSuccess;
+}
+#define cudaFuncSetAttribute(fn, attr, val) (cudaSuccess)

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the partitioned-convolution hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload metric|ir120|...]
+
+Metric: M stereo frames / s ("Msamples/sec stereo conv @ IR=10s/48kHz block=512"): two
+independent mono convolutions (LL, RR — src/dsp/StereoConvolver.cpp:35-36) with their own
+480 000-tap IR each, uniform partitions of 512 (P = 938).  One "step" = one pass of the hot
+path (forward FFT of every block, FDL complex-MAC sweep, inverse FFT + overlap-add) over a batch
+of T blocks of synthetic white noise.
+
+* value            device-resident throughput (input/output already in HBM), CUDA events on the
+                   engine's stream, L2 flushed between steps.
+* e2e              same metric through b200conv_process() with pinned HOST buffers (H2D + D2H in
+                   the timed region, wall clock around the synchronous call).
+* roofline         dominant kernel (k_cmac_batch): algorithmic bytes (16*P*K + 8*K + 16*B
+                   per channel-block, K = 513) / its mean CUDA-event duration vs MEASURED_PEAKS hbm_gbs.
+                   NOTE: the batched sweep reuses H[p] across 16 blocks in registers, so it is
+                   FP32-FMA-bound, not HBM-bound, and `frac` legitimately exceeds 1 — `fp32`
+                   carries the bound that actually applies.
+* cpu_baseline     the reference's own CPU code (oracle/_ref, unmodified sources) on this host.
+N > 1 (torchrun): the IR's partition range is sharded over the ranks, partial spectra are
+summed into rank 0 with one NCCL reduce per batch before the inverse FFT ("strong" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B = 512
+SR = 48000
+WORKLOADS = {
+    # name: (channels, ir seconds, sample rate, block)
+    "metric": dict(C=2, ir_s=10, sr=48000, block=512, desc="stereo 48 kHz, 10 s IR (480000 taps), uniform block 512"),
+    "ir1": dict(C=1, ir_s=1, sr=48000, block=512, desc="mono 48 kHz, 1 s IR, uniform block 512 (config 1)"),
+    "ch8": dict(C=8, ir_s=10, sr=48000, block=512, desc="8-channel 48 kHz, 10 s IR per channel, block 512 (config 4)"),
+    "ir120": dict(C=2, ir_s=120, sr=48000, block=512, desc="stereo 48 kHz, 120 s IR, uniform block 512 (config 5)"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def algorithmic_bytes_per_channel_block(P: int, block: int) -> int:
+    K = block + 1
+    return 16 * P * K + 8 * K + 16 * block
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference timing (oracle/_ref = the unmodified reference sources; falls back to the C port)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, seconds_target: float, threads: int):
+    """Runs `threads` independent stereo (C-channel) instances of the reference's uniform
+    FFTConvolver in parallel, each over the same bounded sample; returns dict for cpu_baseline."""
+    from oracle import oracle as orc
+    kind = "reference" if orc.ref_available() else "port"
+    cls = orc.RefUniform if kind == "reference" else orc.OracleUniform
+    C, block = wl["C"], wl["block"]
+    L = wl["ir_s"] * wl["sr"]
+    irs = [orc.synth_ir(L, c) for c in range(C)]
+
+    def make():
+        convs = []
+        for c in range(C):
+            k = cls()
+            k.init(block, irs[c])
+            convs.append(k)
+        return convs
+
+    # calibrate on one instance
+    convs = make()
+    cal = 16
+    xs = [orc.synth_input(cal * block, c) for c in range(C)]
+    t = time.perf_counter()
+    for c in range(C):
+        convs[c].run(xs[c], block)
+    per_block = (time.perf_counter() - t) / cal          # seconds per stereo block, 1 thread
+    nblk = int(max(32, min(16384, seconds_target / max(per_block, 1e-9))))
+    insts = [convs] + [make() for _ in range(threads - 1)]
+    xs = [orc.synth_input(nblk * block, c) for c in range(C)]
+    done = [0.0] * threads
+
+    def work(i):
+        for c in range(C):           # channels serially on one thread, as StereoConvolver::process does
+            insts[i][c].run(xs[c], block)
+        done[i] = time.perf_counter()
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = max(done) - t0
+    frames = nblk * block * threads
+    return {
+        "value": frames / dt / 1e6, "unit": "M stereo frames/s" if C == 2 else f"M {C}-channel frames/s",
+        "cores": threads, "kind": kind,
+        "sample": f"{threads} independent {C}-channel instances x {nblk} blocks of {block} (ctypes, GIL released), "
+                  f"uniform FFTConvolver, {wl['desc']}",
+        "seconds": dt, "single_thread_ms_per_block": per_block * 1e3,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
+    ap.add_argument("--blocks", type=int, default=0, help="blocks per step (0 = auto)")
+    ap.add_argument("--variant", type=int, default=0, help="CMAC kernel variant (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="print a per-variant timing table to stderr")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload])
+    warm = max(args.warmup, 3)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        # each step = one bounded sample; keep the whole run within a few minutes
+        vals = []
+        for i in range(warm + args.steps):
+            r = cpu_reference_run(wl, seconds_target=2.0 if i < warm else 6.0, threads=threads)
+            if i >= warm:
+                vals.append(r)
+        v = statistics.mean(x["value"] for x in vals)
+        last = vals[-1]
+        line = {
+            "impl": "reference", "metric": "stereo partitioned-convolution throughput (IR 10 s @ 48 kHz, block 512)",
+            "value": v, "unit": "M stereo frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+            "ms_per_step": 1e3 * statistics.mean(x["seconds"] for x in vals), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "engine": "reference CPU FFTConvolver (oracle/_ref)", "threads": threads},
+            "cpu_baseline": {"value": v, "unit": "M stereo frames/s", "cores": threads, "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "M stereo frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from reevr_b200.convolver import Engine
+    from reevr_b200.synth import synth_input, synth_ir
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fall-back)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    C, block = wl["C"], wl["block"]
+    L = wl["ir_s"] * wl["sr"]
+    T = args.blocks or (4736 if args.workload != "ir120" else 1184)
+    n = T * block
+
+    eng = Engine(C, device=local, max_batch_blocks=T + 1, shard_rank=rank, shard_count=world, cmac_variant=args.variant)
+    irs = [synth_ir(L, c) for c in range(C)]
+    t_init = time.perf_counter()
+    assert eng.init_uniform(block, irs)
+    t_init = time.perf_counter() - t_init
+    st = eng.stages()[0]
+    P = int(st["partitions"])
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+    if world > 1:
+        class _Arr:            # zero-copy view of the engine's partial-spectrum buffer
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        def reduce_hook(ptr, nfl, strm):
+            t = torch.as_tensor(_Arr(ptr, nfl), device=torch.device("cuda", local))
+            with torch.cuda.stream(stream):
+                dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            return 0
+        eng.set_reduce(reduce_hook)
+
+    x_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
+    for c in range(C):
+        x_host[c] = torch.from_numpy(synth_input(n, c))
+    y_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
+    x_dev = x_host.cuda(non_blocking=False)
+    y_dev = torch.empty_like(x_dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=False)
+
+    # warm-up
+    for _ in range(warm):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_w0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                       # evict L2 between timed iterations
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ev[i][0].record(stream)
+        step_device()
+        ev[i][1].record(stream)
+    barrier()
+    t_w1 = time.perf_counter()
+    launches = eng.launch_count - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_tot, op=dist.ReduceOp.MAX)
+    total_ms = float(t_tot.item())
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3) / 1e6
+    clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
+
+    # ---- dominant-kernel roofline: CUDA events around every k_cmac_batch launch (separate pass)
+    eng.set_timing(True)
+    cm_ms, cm_n, fft_ms, ifft_ms = 0.0, 0, 0.0, 0.0
+    reps = max(2, min(args.steps, 5))
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=True)
+        tm = eng.last_timing()
+        cm_ms += tm["cmac_ms"]; cm_n += tm["cmac_launches"]; fft_ms += tm["fft_ms"]; ifft_ms += tm["ifft_ms"]
+    eng.set_timing(False)
+    Ploc = int(st["p_end"]) - int(st["p_begin"])
+    peak, peak_kind = measured_peaks()
+    per_launch_ms = cm_ms / max(cm_n, 1)
+    blocks_per_launch = T * reps / max(cm_n, 1)
+    alg_bytes_launch = algorithmic_bytes_per_channel_block(Ploc, block) * C * blocks_per_launch
+    achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    ffma = 4.0 * Ploc * block * C * blocks_per_launch      # 4 FFMA per complex MAC, B bins per row
+    fp32_tflops = 2.0 * ffma / (per_launch_ms * 1e-3) / 1e12
+
+    # ---- end-to-end through the host-pointer C ABI (pinned buffers, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        import ctypes
+        inp = (ctypes.c_void_p * C)(*[x_host[c].data_ptr() for c in range(C)])
+        outp = (ctypes.c_void_p * C)(*[y_host[c].data_ptr() for c in range(C)])
+        for _ in range(2):
+            eng.process_into(inp, outp, n)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.process_into(inp, outp, n)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_val = n * args.steps / float(dt.item()) / 1e6
+        e2e = {"value": e2e_val, "unit": "M stereo frames/s", "h2d_bytes_per_step": C * n * 4,
+               "d2h_bytes_per_step": C * n * 4 if rank == 0 else 0,
+               "how": "b200conv_process() on pinned host buffers, wall clock, 3-stream H2D/compute/D2H pipeline"}
+
+    if args.sweep and rank == 0 and world == 1:
+        for v in (1, 2, 3, 4, 5, 6):
+            e2 = Engine(C, device=local, max_batch_blocks=T + 1, cmac_variant=v)
+            e2.init_uniform(block, irs)
+            e2.set_timing(True)
+            best = 1e9
+            for _ in range(3):
+                e2.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=True)
+                best = min(best, e2.last_timing()["cmac_ms"])
+            print(f"[sweep] variant {v}: cmac {best:.3f} ms  -> {n / best / 1e3:.1f} M frames/s (cmac only)", file=sys.stderr)
+            e2.close()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cpu = cpu_reference_run(wl, seconds_target=12.0, threads=os.cpu_count() or 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread_ms_per_block")}
+        line = {
+            "metric": "stereo partitioned-convolution throughput (IR 10 s @ 48 kHz, block 512)" if args.workload == "metric"
+                      else f"partitioned-convolution throughput ({wl['desc']})",
+            "value": value, "unit": "M stereo frames/s" if C == 2 else f"M {C}-channel frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "channels": C, "ir_taps": eng.ir_len(0), "block": block, "partitions": P,
+                       "blocks_per_step": T, "frames_per_step": n,
+                       "parallelism": "single GPU" if world == 1 else f"partition-range shards x{world} + NCCL reduce of partial spectra",
+                       "l2": "flushed between timed steps (256 MB write)", "init_s": round(t_init, 4)},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": None,
+                         "kernel": "k_cmac_batch", "launch_ms": per_launch_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "note": "algorithmic bytes assume every block streams H and the FDL once (SURVEY §8d); the batched "
+                                 "kernel reuses each H[p][k] for 16 blocks from registers, so frac > 1 is expected and the "
+                                 "binding limit is FP32 FMA issue (see fp32)",
+                         "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                                  "frac": fp32_tflops / (148 * 128 * 2 * 1.965e9 / 1e12),
+                                  "peak_source": "148 SM x 128 FFMA/clk x 2 x 1965 MHz (clocks.max.sm)"},
+                         "step_share": {"cmac_ms": cm_ms / reps, "fft_ms": fft_ms / reps, "ifft_ms": ifft_ms / reps}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -208,20 +208,9 @@ def naive_convolve(x, h) -> np.ndarray:
     return out
 
 
-# ---------------------------------------------------------------------------------------------
-# Synthetic signals of SURVEY.md §8(d) — shared by tests and bench so CPU and GPU see the same bytes.
-# ---------------------------------------------------------------------------------------------
-def synth_ir(n_taps: int, channel: int = 0) -> np.ndarray:
-    """Gaussian noise x exponential decay reaching -60 dB at the last tap, peak-normalised."""
-    rng = np.random.default_rng(4321 + channel)
-    g = rng.standard_normal(n_taps)
-    tau = n_taps / np.log(1000.0)
-    h = g * np.exp(-np.arange(n_taps) / tau)
-    h /= np.max(np.abs(h))
-    return h.astype(np.float32)
+# Synthetic signals of SURVEY.md §8(d) live in the (dependency-free) product module so that
+# bench.py's GPU arm does not have to import anything from oracle/.
+import sys as _sys
 
-
-def synth_input(n: int, channel: int = 0) -> np.ndarray:
-    """White Gaussian noise, sigma = 0.25."""
-    rng = np.random.default_rng(1234 + channel)
-    return (0.25 * rng.standard_normal(n)).astype(np.float32)
+_sys.path.insert(0, os.path.dirname(_HERE))
+from reevr_b200.synth import synth_input, synth_ir  # noqa: E402,F401

@@ -632,7 +632,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   }
   const size_t B0 = h->stages[0].B;
   const size_t chunk = h->Lmax - B0;
-  if (len <= chunk) {
+  if (len <= chunk && len <= std::max((size_t)64 * B0, (size_t)16384)) {
     // latency path: one stream, one group
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));

@@ -97,7 +97,7 @@ struct b200conv {
   // sharding
   b200conv_reduce_fn reduce = nullptr;
   void* reduce_user = nullptr;
-  int smem_optin = 0;
+  int n_sm = 148;
 };
 
 namespace {
@@ -216,10 +216,49 @@ void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
 #endif
 }
 
+constexpr int kStreamNBS = 4;      // blocks per launch the streaming sweep handles
+constexpr int kStreamPW = 8;       // warps per CTA, each striding over the CTA's partition slice
+
+int launch_cmac_stream(b200conv* h, const pc::CmacParams& P, int C) {
+  pc::StreamParams S{};
+  S.H = P.H; S.h_cstride = P.h_cstride;
+  S.X = P.X; S.x_cstride = P.x_cstride; S.xrow0 = P.xrow0;
+  S.Y = P.Y; S.y_cstride = P.y_cstride; S.y_rstride = P.y_rstride; S.yrow0 = P.yrow0;
+  S.B = P.B; S.P = P.Ppad; S.nblocks = P.nblocks;
+  const int ktiles = (P.B / 2 + 31) / 32;
+  // enough CTAs for ~2 per SM, but at least kStreamPW*4 partitions per CTA
+  int nsplit = std::max(1, (2 * h->n_sm) / std::max(1, ktiles * C));
+  nsplit = std::max(1, std::min(nsplit, P.Ppad / (kStreamPW * 4)));
+  S.nsplit = nsplit;
+  if (nsplit > 1) {
+    // rows [yrow0, yrow0+nb) of every channel are contiguous (row pitch C*B)
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_main));
+  }
+  dim3 grid(ktiles, nsplit, C), block(32, kStreamPW, 1);
+  int id = timing_begin(h, kKindCmac);
+#if defined(PC_EMULATE)
+  (void)block;
+  pc::emu_cmac_stream<kStreamNBS, kStreamPW>({(int)grid.x, (int)grid.y, (int)grid.z}, S);
+#else
+  pc::k_cmac_stream<kStreamNBS, kStreamPW><<<grid, block, 0, h->s_main>>>(S);
+#endif
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
 // P.Ppad enters as the number of real (unpadded) partition rows of this shard
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
-  if (variant == 0) variant = (P.nblocks >= 64) ? 1 : 3;
+  if (variant == 0) {
+    if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
+    else variant = (P.nblocks >= 64) ? 1 : 3;
+  }
+  if (variant == 100) {
+    if (P.nblocks > kStreamNBS || P.B < 2) return fail(h, B200CONV_EINVAL, "streaming sweep needs nblocks <= 4 and B >= 2");
+    return launch_cmac_stream(h, P, C);
+  }
   int id = timing_begin(h, kKindCmac);
   switch (variant) {
     case 1: launch_cmac_t<16, 4, 8>(h, P, C); break;
@@ -515,6 +554,12 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
   }
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
+#if !defined(PC_EMULATE)
+  {
+    int sm = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->cfg.device) == cudaSuccess && sm > 0) h->n_sm = sm;
+  }
+#endif
   bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, hi) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;

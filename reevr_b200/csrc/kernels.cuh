@@ -239,6 +239,52 @@ PC_HD void cmac_thread(const float2* __restrict__ Hk,   // &H[c][0][k]
 }
 
 // ------------------------------------------------------------------------------------------
+// K2s: per-thread body of the STREAMING FDL sweep (real-time calls: 1..NBS blocks per launch).
+//   This is the memory-bound form of the reference loop (FFTConvolver.cpp:179-187): every H[p]
+//   and FDL row is read exactly once per block step; a thread owns two adjacent bins (one
+//   16-byte load per operand), a warp strides over the partitions of its CTA's slice
+//   p = p_lo + warp, p_lo + warp + PW, ... and keeps NBS accumulators per bin.
+// ------------------------------------------------------------------------------------------
+struct float4c { float2 a, b; };   // two adjacent bins
+
+PC_HD float4c ld_pair(const float2* p) {
+#if defined(__CUDA_ARCH__)
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  float4c r; r.a = make_float2(v.x, v.y); r.b = make_float2(v.z, v.w); return r;
+#else
+  float4c r; r.a = p[0]; r.b = p[1]; return r;
+#endif
+}
+
+template <int NBS>
+PC_HD void cmac_stream_thread(const float2* __restrict__ Hk,   // &H[c][0][k2]
+                              const float2* __restrict__ Xk,   // &X[c][xrow0][k2] (output 0, partition 0)
+                              long long rowstride, int p_lo, int p_hi, int p_step, int nblocks,
+                              bool packed_first, float2* acc /*[NBS][2]*/) {
+#pragma unroll
+  for (int t = 0; t < NBS; ++t) { acc[2 * t] = make_float2(0.f, 0.f); acc[2 * t + 1] = make_float2(0.f, 0.f); }
+  const float m = packed_first ? 0.0f : 1.0f;
+#pragma unroll 4
+  for (int p = p_lo; p < p_hi; p += p_step) {
+    const float4c h = ld_pair(Hk + (long long)p * rowstride);
+#pragma unroll
+    for (int t = 0; t < NBS; ++t) {
+      if (t < nblocks) {
+        const float4c x = ld_pair(Xk + (long long)(t - p) * rowstride);
+        // first bin: complex, or (DC, Nyquist) as two real products when packed_first
+        float re = fmaf(h.a.x, x.a.x, acc[2 * t].x);
+        re = fmaf(-m * h.a.y, x.a.y, re);
+        float im = packed_first ? fmaf(h.a.y, x.a.y, acc[2 * t].y)
+                                : fmaf(h.a.y, x.a.x, fmaf(h.a.x, x.a.y, acc[2 * t].y));
+        acc[2 * t] = make_float2(re, im);
+        acc[2 * t + 1].x = fmaf(-h.b.y, x.b.y, fmaf(h.b.x, x.b.x, acc[2 * t + 1].x));
+        acc[2 * t + 1].y = fmaf(h.b.y, x.b.x, fmaf(h.b.x, x.b.y, acc[2 * t + 1].y));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // launch parameter blocks (shared by the CUDA kernels and the CPU emulation drivers)
 // ------------------------------------------------------------------------------------------
 struct FwdParams {
@@ -285,6 +331,13 @@ struct InvParams {
   int n_add;
   const float* add[3]; long long add_cstride[3]; long long add_mask[3];
   long long abs0;            // absolute stream position of sample 0 of block 0
+};
+
+struct StreamParams {
+  const float2* H; long long h_cstride;
+  const float2* X; long long x_cstride; long long xrow0;
+  float2* Y; long long y_cstride, y_rstride, yrow0;   // rows must be zero before the launch when nsplit > 1
+  int B, P, nblocks, nsplit;
 };
 
 #if defined(__CUDACC__)
@@ -385,6 +438,48 @@ __global__ void k_inv_fft_ola(InvParams P) {
     for (int s = tx; s < M; s += nth) inv_store(in, M, P.scale, o, s);
   }
 }
+
+// grid (B/64 or 1, nsplit, C), block (32, PW); smem: PW * NBS * 32 * 4 floats (static)
+template <int NBS, int PW>
+__global__ void __launch_bounds__(32 * PW) k_cmac_stream(StreamParams P) {
+  __shared__ float4 red[PW][NBS][32];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int k2 = (blockIdx.x * 32 + lane) * 2;
+  const int c = blockIdx.z;
+  const bool live = k2 < P.B;
+  const int per = (P.P + P.nsplit - 1) / P.nsplit;
+  const int p_lo = blockIdx.y * per;
+  const int p_hi = min(P.P, p_lo + per);
+  float2 acc[2 * NBS];
+  if (live) {
+    const float2* Hk = P.H + (long long)c * P.h_cstride + k2;
+    const float2* Xk = P.X + (long long)c * P.x_cstride + P.xrow0 * (long long)P.B + k2;
+    cmac_stream_thread<NBS>(Hk, Xk, P.B, p_lo + w, p_hi, PW, P.nblocks, k2 == 0, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2 * NBS; ++i) acc[i] = make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int t = 0; t < NBS; ++t) red[w][t][lane] = make_float4(acc[2 * t].x, acc[2 * t].y, acc[2 * t + 1].x, acc[2 * t + 1].y);
+  __syncthreads();
+  // warp w reduces output block t = w, w + PW, ...
+  for (int t = w; t < P.nblocks; t += PW) {
+    float4 v = red[0][t][lane];
+#pragma unroll
+    for (int q = 1; q < PW; ++q) {
+      const float4 u = red[q][t][lane];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (live) {
+      float* y = reinterpret_cast<float*>(P.Y + (long long)c * P.y_cstride + (P.yrow0 + t) * P.y_rstride + k2);
+      if (P.nsplit == 1) {
+        *reinterpret_cast<float4*>(y) = v;
+      } else {
+        atomicAdd(y + 0, v.x); atomicAdd(y + 1, v.y); atomicAdd(y + 2, v.z); atomicAdd(y + 3, v.w);
+      }
+    }
+  }
+}
 #endif  // __CUDACC__
 
 
@@ -474,6 +569,35 @@ inline void emu_inv_fft_ola(EmuDim grid, EmuDim block, const InvParams& P) {
         for (int sidx = 0; sidx < M; ++sidx) inv_store(in, M, P.scale, o, sidx);
       }
   delete[] bufA; delete[] bufB;
+}
+
+template <int NBS, int PW>
+inline void emu_cmac_stream(EmuDim grid, const StreamParams& P) {
+  for (int c = 0; c < grid.z; ++c)
+    for (int by = 0; by < grid.y; ++by)
+      for (int bx = 0; bx < grid.x; ++bx) {
+        const int per = (P.P + P.nsplit - 1) / P.nsplit;
+        const int p_lo = by * per;
+        const int p_hi = P.P < p_lo + per ? P.P : p_lo + per;
+        for (int lane = 0; lane < 32; ++lane) {
+          const int k2 = (bx * 32 + lane) * 2;
+          if (k2 >= P.B) continue;
+          float2 sum[2 * NBS];
+          for (int i = 0; i < 2 * NBS; ++i) sum[i] = make_float2(0.f, 0.f);
+          for (int w = 0; w < PW; ++w) {
+            float2 acc[2 * NBS];
+            const float2* Hk = P.H + (long long)c * P.h_cstride + k2;
+            const float2* Xk = P.X + (long long)c * P.x_cstride + P.xrow0 * (long long)P.B + k2;
+            cmac_stream_thread<NBS>(Hk, Xk, P.B, p_lo + w, p_hi, PW, P.nblocks, k2 == 0, acc);
+            for (int i = 0; i < 2 * NBS; ++i) { sum[i].x += acc[i].x; sum[i].y += acc[i].y; }
+          }
+          for (int t = 0; t < P.nblocks; ++t) {
+            float2* y = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t) * P.y_rstride + k2;
+            if (P.nsplit == 1) { y[0] = sum[2 * t]; y[1] = sum[2 * t + 1]; }
+            else { y[0].x += sum[2 * t].x; y[0].y += sum[2 * t].y; y[1].x += sum[2 * t + 1].x; y[1].y += sum[2 * t + 1].y; }
+          }
+        }
+      }
 }
 #endif  // !__CUDACC__
 

@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing for partition-range sharding.
+
+One process per GPU; rank g owns the partitions [g*ceil(P/G), (g+1)*ceil(P/G)) of every stage:
+it keeps only those IR spectra, recomputes the (tiny) input spectra itself from the broadcast
+input, and produces a PARTIAL spectrum sum.  Between the FDL sweep and the inverse FFT the
+engine calls back into `attach_reduce`'s hook, which sums the partial spectra of all ranks into
+rank 0 with ONE collective per launch group (ncclReduce over NVLink under the "nccl" backend).
+Only rank 0 runs the inverse FFT / overlap-add and produces audio.
+
+The "gloo" branch exists for the world_size-2 CPU tests: with the emulation build of the C ABI
+the "device" pointers are host memory, so the same hook reduces them with gloo.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _CudaView:
+    """Zero-copy __cuda_array_interface__ view of n float32 at a raw device pointer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def attach_reduce(engine, device: int | None = None, group=None, root: int = 0) -> None:
+    """Installs the reduce hook on a sharded Engine (engine.shard_count == world size)."""
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        stream = torch.cuda.ExternalStream(engine.stream, device=dev)
+
+        def hook(ptr: int, n: int, _stream: int) -> int:
+            t = torch.as_tensor(_CudaView(ptr, n), device=dev)
+            with torch.cuda.stream(stream):          # ordered after the sweep, before the inverse FFT
+                dist.reduce(t, dst=root, op=dist.ReduceOp.SUM, group=group)
+            return 0
+    else:
+        def hook(ptr: int, n: int, _stream: int) -> int:
+            buf = (ctypes.c_float * n).from_address(ptr)
+            t = torch.from_numpy(np.ctypeslib.as_array(buf))
+            dist.reduce(t, dst=root, op=dist.ReduceOp.SUM, group=group)
+            return 0
+    engine.set_reduce(hook)

@@ -1,0 +1,123 @@
+"""Partition-range sharding: world_size-2 gloo run on the CPU emulation backend,
+and a single-process sequential fake of the reduce (works on emu and on the GPU)."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as orc
+from reevr_b200.convolver import Engine
+from tests.backends import get_lib, lib  # noqa: F401
+
+TOL = 1e-5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, kind, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from reevr_b200.distributed import attach_reduce
+    lib = get_lib("emu")
+    h = orc.synth_ir(5000)
+    x = orc.synth_input(64 * 90 + 17)
+    e = Engine(1, shard_rank=rank, shard_count=world, max_batch_blocks=32, lib=lib)
+    if kind == "uniform":
+        assert e.init_uniform(64, [h])
+    else:
+        assert e.init_twostage(16, 256, [h])
+    attach_reduce(e)
+    st = e.stages()
+    ys = [e.process([x[i:i + 1000]])[0] for i in range(0, x.size, 1000)]
+    y = np.concatenate(ys)
+    if rank == 0:
+        o = orc.OracleUniform() if kind == "uniform" else orc.OracleTwoStage()
+        o.init(64, h) if kind == "uniform" else o.init(16, 256, h)
+        yo = o.process(x)
+        q.put((float(np.max(np.abs(y - yo)) / np.max(np.abs(yo))), st))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "twostage"])
+def test_two_rank_gloo_partition_shards(kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    err, st = q.get()
+    assert err <= TOL
+    assert st[0]["p_end"] - st[0]["p_begin"] < st[0]["partitions"]     # rank 0 really owns a sub-range
+
+
+def _read(lib_name, ptr, n):
+    if lib_name == "emu":
+        return np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)).copy()
+    from reevr_b200.distributed import _CudaView
+    return torch.as_tensor(_CudaView(ptr, n), device="cuda").clone()
+
+
+def _add(lib_name, ptr, n, vals):
+    if lib_name == "emu":
+        np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))[:] += vals
+    else:
+        from reevr_b200.distributed import _CudaView
+        torch.as_tensor(_CudaView(ptr, n), device="cuda").add_(vals)
+        torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("backend", ["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_sequential_fake_of_the_reduce(backend, G):
+    """Shards 1..G-1 run first and park their partial spectra; shard 0's hook adds them —
+    a faithful single-device stand-in for ncclReduce."""
+    lib_ = get_lib(backend)
+    h = orc.synth_ir(9000)
+    x = orc.synth_input(128 * 40 + 5)
+    calls = [x[:3000], x[3000:]]
+    parked = {}
+
+    def make_hook(rank):
+        state = {"i": 0}
+
+        def hook(ptr, n, stream):
+            if backend == "cuda":
+                torch.cuda.synchronize()
+            i = state["i"]
+            state["i"] += 1
+            if rank != 0:
+                parked.setdefault(i, []).append(_read(backend, ptr, n))
+            else:
+                for v in parked.get(i, []):
+                    _add(backend, ptr, n, v)
+            return 0
+        return hook
+
+    outs = None
+    for rank in list(range(1, G)) + [0]:
+        e = Engine(1, shard_rank=rank, shard_count=G, lib=lib_)
+        assert e.init_uniform(128, [h])
+        e.set_reduce(make_hook(rank))
+        ys = [e.process([c])[0] for c in calls]
+        if rank == 0:
+            outs = np.concatenate(ys)
+    o = orc.OracleUniform()
+    o.init(128, h)
+    yo = o.process(x)
+    assert np.max(np.abs(outs - yo)) / np.max(np.abs(yo)) <= TOL

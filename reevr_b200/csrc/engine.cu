@@ -203,7 +203,7 @@ int launch_inv(b200conv* h, const pc::InvParams& P, int C) {
   return 0;
 }
 
-template <int TT, int D, int TW>
+template <int TT, int D, int TW, int BS = 0>
 void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
   P.Ppad = round_up(P.Ppad, TT);
   dim3 block(32, TW, 1);
@@ -212,8 +212,19 @@ void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
   (void)block;
   pc::emu_cmac_batch<TT, D, TW>({(int)grid.x, (int)grid.y, (int)grid.z}, P);
 #else
-  pc::k_cmac_batch<TT, D, TW><<<grid, block, 0, h->s_main>>>(P);
+  pc::k_cmac_batch<TT, D, TW, BS><<<grid, block, 0, h->s_main>>>(P);
 #endif
+}
+
+// compile-time row pitch for the common block sizes (immediate load offsets), runtime pitch otherwise
+template <int TT, int D, int TW>
+void launch_cmac_bs(b200conv* h, const pc::CmacParams& P, int C) {
+  switch (P.B) {
+    case 128: launch_cmac_t<TT, D, TW, 128>(h, P, C); break;
+    case 512: launch_cmac_t<TT, D, TW, 512>(h, P, C); break;
+    case 8192: launch_cmac_t<TT, D, TW, 8192>(h, P, C); break;
+    default: launch_cmac_t<TT, D, TW, 0>(h, P, C); break;
+  }
 }
 
 constexpr int kStreamNBS = 4;      // blocks per launch the streaming sweep handles
@@ -268,6 +279,9 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     case 5: launch_cmac_t<16, 2, 8>(h, P, C); break;
     case 6: launch_cmac_t<32, 4, 4>(h, P, C); break;
     case 7: launch_cmac_t<4, 4, 8>(h, P, C); break;
+    case 11: launch_cmac_bs<16, 4, 8>(h, P, C); break;
+    case 12: launch_cmac_bs<16, 4, 4>(h, P, C); break;
+    case 16: launch_cmac_bs<32, 4, 4>(h, P, C); break;
     default: return fail(h, B200CONV_EINVAL, "unknown cmac_variant");
   }
   timing_end(h, id);

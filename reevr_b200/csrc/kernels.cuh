@@ -185,12 +185,15 @@ PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int 
 #define PC_LD(p) (*(p))
 #endif
 
-template <int TT, int D>
+//   BS > 0: row pitch known at compile time (B = BS) so that all row offsets inside the unrolled
+//   body become immediate operands of the loads (no per-step 64-bit pointer arithmetic).
+template <int TT, int D, int BS = 0>
 PC_HD void cmac_thread(const float2* __restrict__ Hk,   // &H[c][0][k]
                        const float2* __restrict__ Xk,   // &X[c][xrow0 + t0][k]  (row of output t0, p = 0)
-                       long long rowstride,             // B (float2 elements per row)
+                       long long rowstride_rt,          // B (float2 elements per row)
                        int Ppad, bool packed_bin,
                        float2* acc) {
+  const long long rowstride = BS > 0 ? (long long)BS : rowstride_rt;
   float2 win[TT];
 #pragma unroll
   for (int j = 0; j < TT; ++j) {
@@ -205,15 +208,13 @@ PC_HD void cmac_thread(const float2* __restrict__ Hk,   // &H[c][0][k]
   }
   const float2* hp = Hk + (long long)D * rowstride;       // next H row to prefetch
   const float2* xp = Xk - (long long)(D + 1) * rowstride; // next X row to prefetch
-  for (int p0 = 0; p0 < Ppad; p0 += TT) {
+  for (int p0 = 0; p0 < Ppad; p0 += TT, hp += (long long)TT * rowstride, xp -= (long long)TT * rowstride) {
 #pragma unroll
     for (int u = 0; u < TT; ++u) {
       const float2 h = hq[u % D];
       const float2 xn = xq[u % D];
-      hq[u % D] = PC_LD(hp);
-      xq[u % D] = PC_LD(xp);
-      hp += rowstride;
-      xp -= rowstride;
+      hq[u % D] = PC_LD(hp + (long long)u * rowstride);
+      xq[u % D] = PC_LD(xp - (long long)u * rowstride);
       // logical window entry j lives in win[(j - u) mod TT]
       if (!packed_bin) {
 #pragma unroll
@@ -381,7 +382,7 @@ __global__ void k_fwd_fft(FwdParams P) {
 
 
 // grid (ceil(B/32), ceil(nblocks/(TT*TW)), C), block (32, TW)
-template <int TT, int D, int TW>
+template <int TT, int D, int TW, int BS = 0>
 __global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int t0 = (blockIdx.y * TW + threadIdx.y) * TT;
@@ -390,8 +391,8 @@ __global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
   const float2* Hk = P.H + (long long)c * P.h_cstride + k;
   const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
   float2 acc[TT];
-  if (k == 0) cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, true, acc);
-  else        cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, false, acc);
+  if (k == 0) cmac_thread<TT, D, BS>(Hk, Xk, P.B, P.Ppad, true, acc);
+  else        cmac_thread<TT, D, BS>(Hk, Xk, P.B, P.Ppad, false, acc);
   float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
 #pragma unroll
   for (int j = 0; j < TT; ++j)

@@ -62,7 +62,10 @@ struct Stage {
   int fill = 0;            // samples of the open block already buffered
   float2* H = nullptr;
   float2* X = nullptr;
-  float2* Y = nullptr;
+  float2* Y[2] = {nullptr, nullptr};   // double buffer: the sweep of group i+1 may overlap reduce+IFFT of group i
+  int ybuf = 0;
+  cudaEvent_t ev_sweep[2] = {nullptr, nullptr};   // Y[b] rows written by the sweep
+  cudaEvent_t ev_post[2] = {nullptr, nullptr};    // Y[b] no longer needed by reduce / inverse FFT
   float2* tw = nullptr;
   float* inbuf = nullptr;
   size_t in_stride = 0;
@@ -83,8 +86,9 @@ struct b200conv {
   std::vector<size_t> ir_len;     // post-trim
   size_t Lmax = 0;                // max samples per launch group
   long long abs_pos = 0;          // absolute stream position (samples since init/clear)
-  cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{};
+  cudaStream_t s_main = nullptr, s_post = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{}, ev_din[2]{};
+  cudaEvent_t ev_join = nullptr;
   float* din[2] = {nullptr, nullptr};
   float* dout[2] = {nullptr, nullptr};
   unsigned long long launches = 0;
@@ -115,7 +119,11 @@ namespace {
 int fail(b200conv* h, int code, const std::string& msg) { h->err = msg; return code; }
 
 void free_stage(Stage& s) {
-  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y); cudaFree(s.tw); cudaFree(s.inbuf); cudaFree(s.fut);
+  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y[0]); cudaFree(s.Y[1]); cudaFree(s.tw); cudaFree(s.inbuf); cudaFree(s.fut);
+  for (int i = 0; i < 2; ++i) {
+    if (s.ev_sweep[i]) cudaEventDestroy(s.ev_sweep[i]);
+    if (s.ev_post[i]) cudaEventDestroy(s.ev_post[i]);
+  }
   s = Stage();
 }
 
@@ -134,7 +142,8 @@ void free_all(b200conv* h) {
 // ---- timing helpers ------------------------------------------------------------------------
 enum { kKindFft = 0, kKindCmac = 1, kKindIfft = 2 };
 
-int timing_begin(b200conv* h, int kind) {
+int timing_begin(b200conv* h, int kind, cudaStream_t st = nullptr) {
+  if (!st) st = h->s_main;
   if (!h->timing) return -1;
   if (h->ev_used == h->ev_pool.size()) {
     EventPair p;
@@ -143,11 +152,11 @@ int timing_begin(b200conv* h, int kind) {
   }
   int id = (int)h->ev_used++;
   h->ev_pool[id].kind = kind;
-  cudaEventRecord(h->ev_pool[id].a, h->s_main);
+  cudaEventRecord(h->ev_pool[id].a, st);
   return id;
 }
-void timing_end(b200conv* h, int id) {
-  if (id >= 0) cudaEventRecord(h->ev_pool[id].b, h->s_main);
+void timing_end(b200conv* h, int id, cudaStream_t st = nullptr) {
+  if (id >= 0) cudaEventRecord(h->ev_pool[id].b, st ? st : h->s_main);
 }
 void timing_collect(b200conv* h) {
   h->t_cmac = h->t_fft = h->t_ifft = 0;
@@ -162,24 +171,34 @@ void timing_collect(b200conv* h) {
 }
 
 // ---- kernel launchers ----------------------------------------------------------------------
-void fft_geometry(int M, int nblocks, dim3* grid_xy, dim3* block, size_t* smem) {
-  int tx = std::max(1, std::min(256, M / 4));
-  int ty = std::max(1, 128 / tx);
-  ty = std::min(ty, std::max(1, nblocks));
-  *block = dim3(tx, ty, 1);
-  grid_xy->x = (nblocks + ty - 1) / ty;
-  *smem = (size_t)ty * 2 * M * sizeof(float2);
+// block (tx, ty): tx threads per transform, ty transforms per CTA; see k_fwd_fft
+struct FftGeom { dim3 grid, block; size_t smem; bool warp, tws; };
+
+FftGeom fft_geometry(int M, int nblocks, int C) {
+  FftGeom g;
+  if (M <= 1024) {                       // one warp per transform
+    int ty = std::max(1, std::min(8, 4096 / std::max(M, 1)));
+    ty = std::min(ty, std::max(1, nblocks));
+    g.block = dim3(32, ty, 1);
+    g.warp = true; g.tws = true;
+  } else {                               // whole CTA per transform
+    g.block = dim3(std::min(512, M / 8), 1, 1);
+    g.warp = false; g.tws = (M <= 4096);
+  }
+  g.grid = dim3((nblocks + g.block.y - 1) / g.block.y, C, 1);
+  g.smem = ((g.tws ? 2 * (size_t)M : 0) + (size_t)g.block.y * 2 * M) * sizeof(float2);
+  return g;
 }
 
 int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
-  dim3 grid, block; size_t smem;
-  fft_geometry(P.M, P.nblocks, &grid, &block, &smem);
-  grid.y = C; grid.z = 1;
+  const FftGeom g = fft_geometry(P.M, P.nblocks, C);
   int id = timing_begin(h, kKindFft);
 #if defined(PC_EMULATE)
-  pc::emu_fwd_fft({(int)grid.x, (int)grid.y, 1}, {(int)block.x, (int)block.y, 1}, P);
+  pc::emu_fwd_fft({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  pc::k_fwd_fft<<<grid, block, smem, h->s_main>>>(P);
+  if (g.warp) pc::k_fwd_fft<true, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
+  else if (g.tws) pc::k_fwd_fft<false, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
+  else pc::k_fwd_fft<false, false><<<g.grid, g.block, g.smem, h->s_main>>>(P);
 #endif
   timing_end(h, id);
   h->launches++;
@@ -187,17 +206,17 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
   return 0;
 }
 
-int launch_inv(b200conv* h, const pc::InvParams& P, int C) {
-  dim3 grid, block; size_t smem;
-  fft_geometry(P.M, P.nblocks, &grid, &block, &smem);
-  grid.y = C; grid.z = 1;
-  int id = timing_begin(h, kKindIfft);
+int launch_inv(b200conv* h, const pc::InvParams& P, int C, cudaStream_t st) {
+  const FftGeom g = fft_geometry(P.M, P.nblocks, C);
+  int id = timing_begin(h, kKindIfft, st);
 #if defined(PC_EMULATE)
-  pc::emu_inv_fft_ola({(int)grid.x, (int)grid.y, 1}, {(int)block.x, (int)block.y, 1}, P);
+  pc::emu_inv_fft_ola({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  pc::k_inv_fft_ola<<<grid, block, smem, h->s_main>>>(P);
+  if (g.warp) pc::k_inv_fft_ola<true, true><<<g.grid, g.block, g.smem, st>>>(P);
+  else if (g.tws) pc::k_inv_fft_ola<false, true><<<g.grid, g.block, g.smem, st>>>(P);
+  else pc::k_inv_fft_ola<false, false><<<g.grid, g.block, g.smem, st>>>(P);
 #endif
-  timing_end(h, id);
+  timing_end(h, id, st);
   h->launches++;
   CU_CHECK(h, cudaGetLastError());
   return 0;
@@ -214,6 +233,29 @@ void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
 #else
   pc::k_cmac_batch<TT, D, TW, BS><<<grid, block, 0, h->s_main>>>(P);
 #endif
+}
+
+template <int TT, int D, int TW, int BS, int MINB>
+void launch_cmac2_t(b200conv* h, pc::CmacParams P, int C) {
+  P.Ppad = round_up(P.Ppad, TT);
+  dim3 block(32, TW, 1);
+  dim3 grid((P.B + 31) / 32, (P.nblocks + TT * TW - 1) / (TT * TW), C);
+#if defined(PC_EMULATE)
+  (void)block;
+  pc::emu_cmac_batch2<TT, D, TW>({(int)grid.x, (int)grid.y, (int)grid.z}, P);
+#else
+  pc::k_cmac_batch2<TT, D, TW, BS, MINB><<<grid, block, 0, h->s_main>>>(P);
+#endif
+}
+
+template <int TT, int D, int TW, int MINB>
+void launch_cmac2_bs(b200conv* h, const pc::CmacParams& P, int C) {
+  switch (P.B) {
+    case 128: launch_cmac2_t<TT, D, TW, 128, MINB>(h, P, C); break;
+    case 512: launch_cmac2_t<TT, D, TW, 512, MINB>(h, P, C); break;
+    case 8192: launch_cmac2_t<TT, D, TW, 8192, MINB>(h, P, C); break;
+    default: launch_cmac2_t<TT, D, TW, 0, MINB>(h, P, C); break;
+  }
 }
 
 // compile-time row pitch for the common block sizes (immediate load offsets), runtime pitch otherwise
@@ -282,6 +324,14 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     case 11: launch_cmac_bs<16, 4, 8>(h, P, C); break;
     case 12: launch_cmac_bs<16, 4, 4>(h, P, C); break;
     case 16: launch_cmac_bs<32, 4, 4>(h, P, C); break;
+    case 21: launch_cmac2_bs<16, 4, 4, 4>(h, P, C); break;    // FFMA2, 128 thr/CTA, <=128 regs
+    case 22: launch_cmac2_bs<16, 4, 4, 3>(h, P, C); break;    // FFMA2, 128 thr/CTA, <=168 regs
+    case 23: launch_cmac2_bs<16, 4, 8, 2>(h, P, C); break;    // FFMA2, 256 thr/CTA, <=128 regs
+    case 24: launch_cmac2_bs<16, 2, 4, 4>(h, P, C); break;
+    case 25: launch_cmac2_bs<12, 4, 4, 4>(h, P, C); break;
+    case 26: launch_cmac2_bs<8, 4, 4, 4>(h, P, C); break;
+    case 27: launch_cmac2_bs<16, 4, 2, 8>(h, P, C); break;    // 64 thr/CTA
+    case 28: launch_cmac2_bs<24, 4, 4, 2>(h, P, C); break;
     default: return fail(h, B200CONV_EINVAL, "unknown cmac_variant");
   }
   timing_end(h, id);
@@ -374,7 +424,11 @@ int alloc_stage_state(b200conv* h, Stage& s) {
   s.Tcap = (int)(h->Lmax / B) + 2;
   s.R = 2 * s.hist + s.Tcap + kMaxTT;
   CU_CHECK(h, cudaMalloc(&s.X, (size_t)C * s.R * B * sizeof(float2)));
-  CU_CHECK(h, cudaMalloc(&s.Y, (size_t)(1 + s.Tcap) * C * B * sizeof(float2)));
+  for (int i = 0; i < 2; ++i) {
+    CU_CHECK(h, cudaMalloc(&s.Y[i], (size_t)(1 + s.Tcap) * C * B * sizeof(float2)));
+    CU_CHECK(h, cudaEventCreateWithFlags(&s.ev_sweep[i], cudaEventDisableTiming));
+    CU_CHECK(h, cudaEventCreateWithFlags(&s.ev_post[i], cudaEventDisableTiming));
+  }
   s.in_stride = (size_t)B + h->Lmax;
   CU_CHECK(h, cudaMalloc(&s.inbuf, (size_t)C * s.in_stride * sizeof(float)));
   if (s.q > 0) {
@@ -385,10 +439,13 @@ int alloc_stage_state(b200conv* h, Stage& s) {
 }
 
 int clear_state(b200conv* h) {
+  CU_CHECK(h, cudaStreamSynchronize(h->s_post));
   for (auto& s : h->stages) {
     const int C = h->C, B = s.B;
     CU_CHECK(h, cudaMemsetAsync(s.X, 0, (size_t)C * s.R * B * sizeof(float2), h->s_main));
-    CU_CHECK(h, cudaMemsetAsync(s.Y, 0, (size_t)(1 + s.Tcap) * C * B * sizeof(float2), h->s_main));
+    for (int i = 0; i < 2; ++i)
+      CU_CHECK(h, cudaMemsetAsync(s.Y[i], 0, (size_t)(1 + s.Tcap) * C * B * sizeof(float2), h->s_main));
+    s.ybuf = 0;
     CU_CHECK(h, cudaMemsetAsync(s.inbuf, 0, (size_t)C * s.in_stride * sizeof(float), h->s_main));
     if (s.fut) CU_CHECK(h, cudaMemsetAsync(s.fut, 0, (size_t)C * s.ring * sizeof(float), h->s_main));
     s.head = s.hist;
@@ -403,6 +460,7 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
                 const float* const* ir, const size_t* ir_len) {
   if (int rc = set_device(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  CU_CHECK(h, cudaStreamSynchronize(h->s_post));
   free_all(h);
   const int C = h->C;
   for (int s = 0; s < n_stages; ++s)
@@ -460,13 +518,18 @@ int compact_timeline(b200conv* h, Stage& s) {
   return 0;
 }
 
-int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n) {
+// `overlap`: reduce + inverse FFT go to s_post so that they overlap the next group's forward
+// FFT + sweep on s_main (double-buffered Y); otherwise everything is issued on s_main.
+int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n,
+              bool overlap) {
   const int C = h->C;
   const bool root = h->cfg.shard_rank == 0;
+  cudaStream_t ps = overlap ? h->s_post : h->s_main;
   // stages >= 1 first (their look-ahead output may be consumed by the head within this group)
   for (int si = (int)h->stages.size() - 1; si >= 0; --si) {
     Stage& s = h->stages[si];
     const int B = s.B;
+    const size_t row = (size_t)C * B;           // float2 per Y row (all channels)
     // append the new samples behind the open block's samples
     CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
                                   n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
@@ -474,6 +537,8 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
     const int complete = (int)(total / B);
     const int partial = (int)(total % B);
     const int nb = (si == 0) ? complete + (partial > 0 ? 1 : 0) : complete;
+    const int yb = s.ybuf;
+    float2* Yb = s.Y[yb];
     if (nb > 0) {
       if (s.head + nb + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
       pc::FwdParams fp{};
@@ -482,21 +547,27 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
       fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
       if (int rc = launch_fwd(h, fp, C)) return rc;
 
+      // Y[yb] rows >= 1 may still be read by the post work of two groups ago
+      if (overlap) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb], 0));
       pc::CmacParams cp{};
       cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
       cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
-      cp.Y = s.Y; cp.y_cstride = B; cp.y_rstride = (long long)C * B; cp.yrow0 = 1;
+      cp.Y = Yb; cp.y_cstride = B; cp.y_rstride = (long long)row; cp.yrow0 = 1;
       cp.B = B; cp.Ppad = s.P; cp.nblocks = nb;
       if (int rc = launch_cmac(h, cp, C)) return rc;
+      if (overlap) {
+        CU_CHECK(h, cudaEventRecord(s.ev_sweep[yb], h->s_main));
+        CU_CHECK(h, cudaStreamWaitEvent(ps, s.ev_sweep[yb], 0));
+      }
 
       if (h->cfg.shard_count > 1) {
         if (!h->reduce) return fail(h, B200CONV_ESTATE, "sharded handle without a reduce hook");
-        if (h->reduce(h->reduce_user, reinterpret_cast<float*>(s.Y + (size_t)C * B), (size_t)nb * C * B * 2, h->s_main) != 0)
+        if (h->reduce(h->reduce_user, reinterpret_cast<float*>(Yb + row), (size_t)nb * row * 2, ps) != 0)
           return fail(h, B200CONV_ECUDA, "reduce hook failed");
       }
       if (root) {
         pc::InvParams ip{};
-        ip.Y = s.Y; ip.y_cstride = B; ip.y_rstride = (long long)C * B; ip.yrow0 = 1;
+        ip.Y = Yb; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
         ip.tw = s.tw; ip.M = B; ip.nblocks = nb; ip.scale = 1.0f / (float)B;
         if (si == 0) {
           ip.dst = out_dev; ip.dst_cstride = (long long)out_stride;
@@ -515,23 +586,36 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
           ip.lo = 0; ip.hi = (long long)1 << 62; ip.mask = (long long)s.ring - 1;
           ip.n_add = 0; ip.abs0 = 0;
         }
-        if (int rc = launch_inv(h, ip, C)) return rc;
+        if (int rc = launch_inv(h, ip, C, ps)) return rc;
       }
     }
     // state update
     if (complete > 0) {
-      CU_CHECK(h, cudaMemcpyAsync(s.Y, s.Y + (size_t)complete * C * B, (size_t)C * B * sizeof(float2),
-                                  cudaMemcpyDeviceToDevice, h->s_main));
+      // overlap state for the next group: last completed row -> row 0 of the buffer it will use
+      const int nxt = overlap ? (yb ^ 1) : yb;
+      CU_CHECK(h, cudaMemcpyAsync(s.Y[nxt], Yb + (size_t)complete * row, row * sizeof(float2),
+                                  cudaMemcpyDeviceToDevice, ps));
+      if (overlap) CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
+      s.ybuf = nxt;
       if (partial > 0)
         CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), s.inbuf + (size_t)complete * B,
                                       s.in_stride * sizeof(float), partial * sizeof(float), C,
                                       cudaMemcpyDeviceToDevice, h->s_main));
       s.head += complete;
       s.blocks_done += complete;
+    } else if (overlap && nb > 0) {
+      CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
     }
     s.fill = partial;
   }
   h->abs_pos += (long long)n;
+  return 0;
+}
+
+// make s_main wait for everything queued on s_post (end of an overlapped call)
+int join_post(b200conv* h) {
+  CU_CHECK(h, cudaEventRecord(h->ev_join, h->s_post));
+  CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
   return 0;
 }
 
@@ -575,18 +659,26 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
   }
 #endif
   bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&h->s_post, cudaStreamNonBlocking, hi) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i) {
     ok = ok && cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_din[i], cudaEventDisableTiming) == cudaSuccess;
   }
 #if !defined(PC_EMULATE)
   if (ok) {
-    // the FFT kernels need up to 128 KB of dynamic shared memory (B = 8192)
-    ok = cudaFuncSetAttribute(pc::k_fwd_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+    // the FFT kernels need up to 192 KB of dynamic shared memory (B = 4096: table + ping-pong buffers)
+    const int kSmem = 200 * 1024;
+    ok = cudaFuncSetAttribute(pc::k_fwd_fft<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
   }
 #endif
   if (!ok) {
@@ -601,13 +693,17 @@ void b200conv_destroy(b200conv_t* h) {
   if (!h->sticky_cuda_error || h->s_main) {
     cudaSetDevice(h->cfg.device);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
+    if (h->s_post) cudaStreamSynchronize(h->s_post);
     free_all(h);
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {
       if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
       if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
       if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+      if (h->ev_din[i]) cudaEventDestroy(h->ev_din[i]);
     }
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->s_post) cudaStreamDestroy(h->s_post);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -664,13 +760,15 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
     if (len) CU_CHECK(h, cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, len * sizeof(float), h->C, h->s_main));
   } else {
     const size_t B0 = h->stages[0].B;
+    const size_t chunk = h->Lmax - B0;     // keeps fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
+    const bool overlap = len > chunk || h->cfg.shard_count > 1;
     size_t done = 0;
     while (done < len) {
-      // keep fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
-      size_t n = std::min(len - done, h->Lmax - B0);
-      if (int rc = run_group(h, in_dev + done, in_stride, out_dev + done, out_stride, n)) return rc;
+      size_t n = std::min(len - done, chunk);
+      if (int rc = run_group(h, in_dev + done, in_stride, out_dev + done, out_stride, n, overlap)) return rc;
       done += n;
     }
+    if (overlap) { if (int rc = join_post(h)) return rc; }
   }
   if (sync || h->timing) {
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
@@ -695,7 +793,9 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     // latency path: one stream, one group
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
-    if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len)) return rc;
+    const bool ov = h->cfg.shard_count > 1;
+    if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len, ov)) return rc;
+    if (ov) { if (int rc = join_post(h)) return rc; }
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
@@ -709,14 +809,15 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   for (; done < len; ++i) {
     const int b = i & 1;
     const size_t n = std::min(len - done, grp);
-    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));     // din[b] free again
+    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_din[b], 0));     // din[b] free again
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * h->Lmax, in[c] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
     CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
     CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_h2d[b], 0));
-    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_d2h[b], 0));    // dout[b] drained
-    if (int rc = run_group(h, h->din[b], h->Lmax, h->dout[b], h->Lmax, n)) return rc;
-    CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_main));
+    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_post, h->ev_d2h[b], 0));    // dout[b] drained
+    if (int rc = run_group(h, h->din[b], h->Lmax, h->dout[b], h->Lmax, n, true)) return rc;
+    CU_CHECK(h, cudaEventRecord(h->ev_din[b], h->s_main));    // every read of din[b] is queued on s_main
+    CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_post));    // dout[b] complete
     CU_CHECK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(out[c] + done, h->dout[b] + (size_t)c * h->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
@@ -724,6 +825,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     done += n;
   }
   CU_CHECK(h, cudaStreamSynchronize(h->s_out));
+  if (int rc = join_post(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return B200CONV_OK;
 }
@@ -740,6 +842,7 @@ int b200conv_reset(b200conv_t* h) {
   REQUIRE_CUDA(h);
   if (int rc = set_device(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  CU_CHECK(h, cudaStreamSynchronize(h->s_post));
   free_all(h);
   return B200CONV_OK;
 }

@@ -46,13 +46,31 @@ PC_HD float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
 
 PC_HD int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// radix of the Stockham pass that starts with sub-transform length p (M total): one radix-2
-// pass first when log2(M/p) is odd, radix-4 otherwise.
-PC_HD int pass_radix(int M, int p) { return (ilog2(M / p) & 1) ? 2 : 4; }
+// radix of the Stockham pass that starts with sub-transform length p (M total):
+// radix-8 wherever possible, the remainder as 4*4 / 4 / 2  (M = 512 -> 8,8,8; 128 -> 8,4,4; 8192 -> 8,8,8,4,4)
+PC_HD int pass_radix(int M, int p) {
+  const int l = ilog2(M / p);
+  if (l == 1) return 2;
+  if (l == 2 || l == 4) return 4;
+  return 8;
+}
+
+// 4-point DFT in place (forward: e^{-2*pi*i/4}; INV: conjugate)
+template <bool INV>
+PC_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 b0 = c_add(a0, a2), b1 = c_sub(a0, a2), b2 = c_add(a1, a3);
+  const float2 d = c_sub(a1, a3);
+  const float2 b3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);   // -/+ i * d
+  a0 = c_add(b0, b2);
+  a1 = c_add(b1, b3);
+  a2 = c_sub(b0, b2);
+  a3 = c_sub(b1, b3);
+}
 
 // ------------------------------------------------------------------------------------------
 // One Stockham autosort pass, out of place (in -> out), butterfly i in [0, M/R).
 // tw = exp(-2*pi*i*j/(2M)), j < 2M (full circle of the REAL transform size N = 2M).
+//   k = i mod p ; inputs in[i + r*M/R] * w^(r*k), w = exp(-2*pi*i/(p*R)) ; outputs out[(i-k)*R + k + m*p]
 // ------------------------------------------------------------------------------------------
 template <bool INV>
 PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, int M, int p, int R, int i) {
@@ -60,7 +78,43 @@ PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, i
   const int j = (i - k) * R + k;
   const int stride = M / R;
   const int tstep = (2 * M) / (p * R);          // table step for exp(-2*pi*i*k/(p*R))
-  if (R == 4) {
+  if (R == 8) {
+    float2 a[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = in[i + r * stride];
+    if (k != 0) {
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        float2 w = tw[r * k * tstep];
+        if (INV) w.y = -w.y;
+        a[r] = c_mul(a[r], w);
+      }
+    }
+    // radix-2 stage on (r, r+4), then W8 twiddles on the odd half, then two DFT4
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float2 s = c_add(a[r], a[r + 4]), d = c_sub(a[r], a[r + 4]);
+      a[r] = s; a[r + 4] = d;
+    }
+    const float h = 0.70710678118654752440f;
+    // a5 *= W8^1, a6 *= W8^2, a7 *= W8^3   (forward W8 = e^{-i*pi/4}; inverse conjugate)
+    if (!INV) {
+      a[5] = make_float2(h * (a[5].x + a[5].y), h * (a[5].y - a[5].x));
+      a[6] = make_float2(a[6].y, -a[6].x);
+      a[7] = make_float2(h * (a[7].y - a[7].x), -h * (a[7].x + a[7].y));
+    } else {
+      a[5] = make_float2(h * (a[5].x - a[5].y), h * (a[5].x + a[5].y));
+      a[6] = make_float2(-a[6].y, a[6].x);
+      a[7] = make_float2(-h * (a[7].x + a[7].y), h * (a[7].x - a[7].y));
+    }
+    dft4<INV>(a[0], a[1], a[2], a[3]);     // even outputs X[0], X[2], X[4], X[6]
+    dft4<INV>(a[4], a[5], a[6], a[7]);     // odd outputs  X[1], X[3], X[5], X[7]
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      out[j + (2 * m) * p] = a[m];
+      out[j + (2 * m + 1) * p] = a[4 + m];
+    }
+  } else if (R == 4) {
     float2 a0 = in[i];
     float2 a1 = in[i + stride];
     float2 a2 = in[i + 2 * stride];
@@ -70,14 +124,11 @@ PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, i
       if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       a1 = c_mul(a1, w1); a2 = c_mul(a2, w2); a3 = c_mul(a3, w3);
     }
-    const float2 b0 = c_add(a0, a2), b1 = c_sub(a0, a2), b2 = c_add(a1, a3);
-    const float2 d = c_sub(a1, a3);
-    // forward: -i*d ; inverse: +i*d
-    const float2 b3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-    out[j] = c_add(b0, b2);
-    out[j + p] = c_add(b1, b3);
-    out[j + 2 * p] = c_sub(b0, b2);
-    out[j + 3 * p] = c_sub(b1, b3);
+    dft4<INV>(a0, a1, a2, a3);
+    out[j] = a0;
+    out[j + p] = a1;
+    out[j + 2 * p] = a2;
+    out[j + 3 * p] = a3;
   } else {
     float2 a0 = in[i];
     float2 a1 = in[i + stride];
@@ -166,7 +217,9 @@ PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int 
   if (idx < o.lo || idx >= o.hi) return;
   const float2 v = z[s >> 1];
   float r = ((s & 1) ? v.y : v.x) * scale;
-  for (int a = 0; a < o.n_add; ++a) r += o.add[a][(o.abs0 + s) & o.add_mask[a]];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (a < o.n_add) r += o.add[a][(o.abs0 + s) & o.add_mask[a]];
   o.dst[idx & o.mask] = r;
 }
 
@@ -237,6 +290,66 @@ PC_HD void cmac_thread(const float2* __restrict__ Hk,   // &H[c][0][k]
       win[(TT - 1 - u + TT) % TT] = xn;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (packed-FMA form): same tiling as cmac_thread, arithmetic on sm_100's 2-wide FP32 FMA
+// (fma.rn.f32x2 / SASS FFMA2).  Per output block two float2 accumulators:
+//     A += (h.re, h.re) * (x.re, x.im)        B += (h.im, h.im) * (x.re, x.im)
+//   => re = A.re - B.im ,  im = A.im + B.re          (complex bins)
+//      re = A.re        ,  im = B.im                 (entry 0 = the two real bins DC / Nyquist)
+// so the inner loop is identical for every bin (no divergence on the packed entry), half the
+// issue slots of the scalar form (32 FFMA2 instead of 64 FFMA per partition) and every operand
+// is an aligned 64-bit register pair (no even/odd register-bank conflicts between x and acc).
+// ------------------------------------------------------------------------------------------
+PC_HD float2 ffma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
+template <int TT, int D, int BS = 0>
+PC_HD void cmac_thread2(const float2* __restrict__ Hk, const float2* __restrict__ Xk, long long rowstride_rt,
+                        int Ppad, bool packed_bin, float2* out) {
+  const long long rowstride = BS > 0 ? (long long)BS : rowstride_rt;
+  float2 win[TT], accA[TT], accB[TT];
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    win[j] = PC_LD(Xk + (long long)j * rowstride);
+    accA[j] = make_float2(0.0f, 0.0f);
+    accB[j] = make_float2(0.0f, 0.0f);
+  }
+  float2 hq[D], xq[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    hq[d] = PC_LD(Hk + (long long)d * rowstride);
+    xq[d] = PC_LD(Xk - (long long)(d + 1) * rowstride);
+  }
+  const float2* hp = Hk + (long long)D * rowstride;
+  const float2* xp = Xk - (long long)(D + 1) * rowstride;
+  for (int p0 = 0; p0 < Ppad; p0 += TT, hp += (long long)TT * rowstride, xp -= (long long)TT * rowstride) {
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+      const float2 h = hq[u % D];
+      const float2 xn = xq[u % D];
+      hq[u % D] = PC_LD(hp + (long long)u * rowstride);
+      xq[u % D] = PC_LD(xp - (long long)u * rowstride);
+      const float2 hr = make_float2(h.x, h.x), hi = make_float2(h.y, h.y);
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        const float2 x = win[(j - u + TT) % TT];
+        accA[j] = ffma2(hr, x, accA[j]);
+        accB[j] = ffma2(hi, x, accB[j]);
+      }
+      win[(TT - 1 - u + TT) % TT] = xn;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TT; ++j)
+    out[j] = packed_bin ? make_float2(accA[j].x, accB[j].y)
+                        : make_float2(accA[j].x - accB[j].y, accA[j].y + accB[j].x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -347,7 +460,17 @@ struct StreamParams {
 // ==========================================================================================
 
 
-// grid (ceil(nblocks/ty), C), block (tx, ty); dynamic smem = ty * 2 * M * sizeof(float2)
+// FFT kernel geometry: block (tx, ty) = tx threads per transform, ty transforms per CTA.
+//   WARP = true : tx == 32, one warp owns one transform -> passes are separated by __syncwarp()
+//                 only (no CTA-wide barrier after the twiddle preload), warps run decoupled.
+//   TWS  = true : the twiddle table (2M float2) is staged in shared memory once per CTA.
+// dynamic smem = (TWS ? 2M : 0) + ty * 2M float2.  grid (ceil(nblocks/ty), C).
+template <bool WARP>
+__device__ __forceinline__ void fft_sync() {
+  if (WARP) __syncwarp(); else __syncthreads();
+}
+
+template <bool WARP, bool TWS>
 __global__ void k_fwd_fft(FwdParams P) {
   extern __shared__ float2 pc_smem[];
   const int M = P.M;
@@ -355,7 +478,15 @@ __global__ void k_fwd_fft(FwdParams P) {
   const int blk = blockIdx.x * blockDim.y + threadIdx.y;
   const int c = blockIdx.y;
   const bool active = blk < P.nblocks;
-  float2* bufA = pc_smem + (size_t)threadIdx.y * 2 * M;
+  const float2* tw = P.tw;
+  float2* data = pc_smem;
+  if (TWS) {
+    const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
+    for (int j = tid; j < 2 * M; j += nthr) pc_smem[j] = P.tw[j];
+    tw = pc_smem;
+    data = pc_smem + 2 * M;
+  }
+  float2* bufA = data + (size_t)threadIdx.y * 2 * M;
   float2* bufB = bufA + M;
   if (active) {
     const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
@@ -364,19 +495,19 @@ __global__ void k_fwd_fft(FwdParams P) {
     const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
     for (int n = tx; n < M; n += nth) fwd_load(src, nv, bufA, M, n);
   }
-  __syncthreads();
+  __syncthreads();                      // twiddles staged, transform loaded
   float2* in = bufA; float2* out = bufB;
   for (int p = 1; p < M;) {
     const int R = pass_radix(M, p);
     if (active)
-      for (int i = tx; i < M / R; i += nth) stockham_butterfly<false>(in, out, P.tw, M, p, R, i);
-    __syncthreads();
+      for (int i = tx; i < M / R; i += nth) stockham_butterfly<false>(in, out, tw, M, p, R, i);
+    fft_sync<WARP>();
     float2* t = in; in = out; out = t;
     p *= R;
   }
   if (active) {
     float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
-    for (int k = tx; k <= M / 2; k += nth) fwd_split(in, X, P.tw, M, k);
+    for (int k = tx; k <= M / 2; k += nth) fwd_split(in, X, tw, M, k);
   }
 }
 
@@ -400,7 +531,8 @@ __global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
 }
 
 
-// grid (ceil(nblocks/ty), C), block (tx, ty); dynamic smem = ty * 2 * M * sizeof(float2)
+// same geometry as k_fwd_fft
+template <bool WARP, bool TWS>
 __global__ void k_inv_fft_ola(InvParams P) {
   extern __shared__ float2 pc_smem[];
   const int M = P.M;
@@ -408,20 +540,29 @@ __global__ void k_inv_fft_ola(InvParams P) {
   const int blk = blockIdx.x * blockDim.y + threadIdx.y;
   const int c = blockIdx.y;
   const bool active = blk < P.nblocks;
-  float2* bufA = pc_smem + (size_t)threadIdx.y * 2 * M;
+  const float2* tw = P.tw;
+  float2* data = pc_smem;
+  if (TWS) {
+    const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
+    for (int j = tid; j < 2 * M; j += nthr) pc_smem[j] = P.tw[j];
+    tw = pc_smem;
+    data = pc_smem + 2 * M;
+    __syncthreads();                    // inv_pre already needs the table
+  }
+  float2* bufA = data + (size_t)threadIdx.y * 2 * M;
   float2* bufB = bufA + M;
   if (active) {
     const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
     const float2* Yp = Yt - P.y_rstride;
-    for (int k = tx; k <= M / 2; k += nth) inv_pre(Yt, Yp, bufA, P.tw, M, k);
+    for (int k = tx; k <= M / 2; k += nth) inv_pre(Yt, Yp, bufA, tw, M, k);
   }
-  __syncthreads();
+  fft_sync<WARP>();
   float2* in = bufA; float2* out = bufB;
   for (int p = 1; p < M;) {
     const int R = pass_radix(M, p);
     if (active)
-      for (int i = tx; i < M / R; i += nth) stockham_butterfly<true>(in, out, P.tw, M, p, R, i);
-    __syncthreads();
+      for (int i = tx; i < M / R; i += nth) stockham_butterfly<true>(in, out, tw, M, p, R, i);
+    fft_sync<WARP>();
     float2* t = in; in = out; out = t;
     p *= R;
   }
@@ -438,6 +579,23 @@ __global__ void k_inv_fft_ola(InvParams P) {
     o.abs0 = P.abs0 + (long long)blk * M;
     for (int s = tx; s < M; s += nth) inv_store(in, M, P.scale, o, s);
   }
+}
+
+// packed-FMA variant; MINB = CTAs per SM the register allocation must allow
+template <int TT, int D, int TW, int BS, int MINB>
+__global__ void __launch_bounds__(32 * TW, MINB) k_cmac_batch2(CmacParams P) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = (blockIdx.y * TW + threadIdx.y) * TT;
+  const int c = blockIdx.z;
+  if (k >= P.B || t0 >= P.nblocks) return;
+  const float2* Hk = P.H + (long long)c * P.h_cstride + k;
+  const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
+  float2 acc[TT];
+  cmac_thread2<TT, D, BS>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
+  float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
+#pragma unroll
+  for (int j = 0; j < TT; ++j)
+    if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
 }
 
 // grid (B/64 or 1, nsplit, C), block (32, PW); smem: PW * NBS * 32 * 4 floats (static)
@@ -532,6 +690,26 @@ inline void emu_cmac_batch(EmuDim grid, const CmacParams& P) {
             const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
             float2 acc[TT];
             cmac_thread<TT, D>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
+            float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
+            for (int j = 0; j < TT; ++j)
+              if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
+          }
+}
+
+template <int TT, int D, int TW>
+inline void emu_cmac_batch2(EmuDim grid, const CmacParams& P) {
+  for (int c = 0; c < grid.z; ++c)
+    for (int by = 0; by < grid.y; ++by)
+      for (int bx = 0; bx < grid.x; ++bx)
+        for (int w = 0; w < TW; ++w)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int k = bx * 32 + lane;
+            const int t0 = (by * TW + w) * TT;
+            if (k >= P.B || t0 >= P.nblocks) continue;
+            const float2* Hk = P.H + (long long)c * P.h_cstride + k;
+            const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
+            float2 acc[TT];
+            cmac_thread2<TT, D>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
             float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
             for (int j = 0; j < TT; ++j)
               if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];

@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="print a per-variant timing table to stderr")
+    ap.add_argument("--also-ir120", dest="also_ir120", action="store_true",
+                    help="additionally time config 5 (120 s IR) and attach it as `ir120`")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,46 +221,15 @@ def main():
     import torch
     import torch.distributed as dist
     from reevr_b200.convolver import Engine
+    from reevr_b200.distributed import attach_reduce
     from reevr_b200.synth import synth_input, synth_ir
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fall-back)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    C, block = wl["C"], wl["block"]
-    L = wl["ir_s"] * wl["sr"]
-    T = args.blocks or (7104 if args.workload != "ir120" else 1776)
-    n = T * block
-
-    eng = Engine(C, device=local, max_batch_blocks=T + 1, shard_rank=rank, shard_count=world, cmac_variant=args.variant)
-    irs = [synth_ir(L, c) for c in range(C)]
-    t_init = time.perf_counter()
-    assert eng.init_uniform(block, irs)
-    t_init = time.perf_counter() - t_init
-    st = eng.stages()[0]
-    P = int(st["partitions"])
-    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
-
-    if world > 1:
-        class _Arr:            # zero-copy view of the engine's partial-spectrum buffer
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-        def reduce_hook(ptr, nfl, strm):
-            t = torch.as_tensor(_Arr(ptr, nfl), device=torch.device("cuda", local))
-            with torch.cuda.stream(stream):
-                dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-            return 0
-        eng.set_reduce(reduce_hook)
-
-    x_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
-    for c in range(C):
-        x_host[c] = torch.from_numpy(synth_input(n, c))
-    y_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
-    x_dev = x_host.cuda(non_blocking=False)
-    y_dev = torch.empty_like(x_dev)
+        dist.init_process_group("nccl", device_id=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -266,129 +237,161 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=False)
-
-    # warm-up
-    for _ in range(warm):
-        step_device()
-    barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    launches0 = eng.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_w0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()                       # evict L2 between timed iterations
-        torch.cuda.synchronize()
+    def run_workload(wl, T, steps, with_e2e, with_clocks):
+        """Times one workload; returns the dict the JSON line is assembled from (rank 0) / None."""
+        C, block = wl["C"], wl["block"]
+        L = wl["ir_s"] * wl["sr"]
+        n = T * block
+        # single GPU: one launch group per step; sharded: 3 groups so that the NCCL reduce + inverse FFT of
+        # group i overlap the sweep of group i+1 (engine post stream)
+        groups = 1 if world == 1 else 3
+        gb = (T + groups - 1) // groups
+        eng = Engine(C, device=local, max_batch_blocks=gb + 1, shard_rank=rank, shard_count=world, cmac_variant=args.variant)
+        irs = [synth_ir(L, c) for c in range(C)]
+        t_init = time.perf_counter()
+        assert eng.init_uniform(block, irs)
+        t_init = time.perf_counter() - t_init
+        st = eng.stages()[0]
+        P = int(st["partitions"])
+        Ploc = int(st["p_end"]) - int(st["p_begin"])
+        stream = torch.cuda.ExternalStream(eng.stream, device=dev)
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        ev[i][0].record(stream)
-        step_device()
-        ev[i][1].record(stream)
-    barrier()
-    t_w1 = time.perf_counter()
-    launches = eng.launch_count - launches0
-    ms = [a.elapsed_time(b) for a, b in ev]
-    t_tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_tot, op=dist.ReduceOp.MAX)
-    total_ms = float(t_tot.item())
-    ms_per_step = total_ms / args.steps
-    value = n / (ms_per_step * 1e-3) / 1e6
-    clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
+            attach_reduce(eng, device=local)
 
-    # ---- dominant-kernel roofline: CUDA events around every k_cmac_batch launch (separate pass)
-    eng.set_timing(True)
-    cm_ms, cm_n, fft_ms, ifft_ms = 0.0, 0, 0.0, 0.0
-    reps = max(2, min(args.steps, 5))
-    for _ in range(reps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=True)
-        tm = eng.last_timing()
-        cm_ms += tm["cmac_ms"]; cm_n += tm["cmac_launches"]; fft_ms += tm["fft_ms"]; ifft_ms += tm["ifft_ms"]
-    eng.set_timing(False)
-    Ploc = int(st["p_end"]) - int(st["p_begin"])
-    peak, peak_kind = measured_peaks()
-    per_launch_ms = cm_ms / max(cm_n, 1)
-    blocks_per_launch = T * reps / max(cm_n, 1)
-    alg_bytes_launch = algorithmic_bytes_per_channel_block(Ploc, block) * C * blocks_per_launch
-    achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
-    ffma = 4.0 * Ploc * block * C * blocks_per_launch      # 4 FFMA per complex MAC, B bins per row
-    fp32_tflops = 2.0 * ffma / (per_launch_ms * 1e-3) / 1e12
+        x_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
+        for c in range(C):
+            x_host[c] = torch.from_numpy(synth_input(n, c))
+        y_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
+        x_dev = x_host.cuda(non_blocking=False)
+        y_dev = torch.empty_like(x_dev)
 
-    # ---- end-to-end through the host-pointer C ABI (pinned buffers, H2D + D2H inside the timed region)
-    e2e = None
-    if not args.no_e2e:
-        import ctypes
-        inp = (ctypes.c_void_p * C)(*[x_host[c].data_ptr() for c in range(C)])
-        outp = (ctypes.c_void_p * C)(*[y_host[c].data_ptr() for c in range(C)])
-        for _ in range(2):
-            eng.process_into(inp, outp, n)
+        def step_device():
+            eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=False)
+
+        for _ in range(warm):
+            step_device()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.process_into(inp, outp, n)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        sampler = ClockSampler(local) if (with_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        launches0 = eng.launch_count
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t_w0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()                       # evict L2 between timed iterations
+            barrier()
+            ev[i][0].record(stream)
+            step_device()
+            ev[i][1].record(stream)
+        barrier()
+        t_w1 = time.perf_counter()
+        launches = eng.launch_count - launches0
+        t_tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_val = n * args.steps / float(dt.item()) / 1e6
-        e2e = {"value": e2e_val, "unit": "M stereo frames/s", "h2d_bytes_per_step": C * n * 4,
-               "d2h_bytes_per_step": C * n * 4 if rank == 0 else 0,
-               "how": "b200conv_process() on pinned host buffers, wall clock, 3-stream H2D/compute/D2H pipeline"}
+            dist.all_reduce(t_tot, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t_tot.item()) / steps
+        value = n / (ms_per_step * 1e-3) / 1e6
+        clocks = sampler.stop(t_w0, t_w1) if sampler else None
+
+        # dominant-kernel roofline: CUDA events around every FDL-sweep launch (separate pass)
+        eng.set_timing(True)
+        cm_ms, cm_n, fft_ms, ifft_ms = 0.0, 0, 0.0, 0.0
+        reps = max(2, min(steps, 5))
+        for _ in range(reps):
+            flush.zero_()
+            barrier()
+            eng.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=True)
+            tm = eng.last_timing()
+            cm_ms += tm["cmac_ms"]; cm_n += tm["cmac_launches"]; fft_ms += tm["fft_ms"]; ifft_ms += tm["ifft_ms"]
+        eng.set_timing(False)
+        peak, peak_kind = measured_peaks()
+        per_launch_ms = cm_ms / max(cm_n, 1)
+        blocks_per_launch = T * reps / max(cm_n, 1)
+        alg_bytes_launch = algorithmic_bytes_per_channel_block(Ploc, block) * C * blocks_per_launch
+        achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        ffma = 4.0 * Ploc * block * C * blocks_per_launch      # 4 FP32 FMA per complex MAC, B bins per row
+        fp32_tflops = 2.0 * ffma / (per_launch_ms * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            key = f"{args.workload if wl is WL0 else 'ir120'}:T{int(blocks_per_launch)}:G{world}"
+            traffic = tj.get(key)
+
+        e2e = None
+        if with_e2e:
+            import ctypes
+            inp = (ctypes.c_void_p * C)(*[x_host[c].data_ptr() for c in range(C)])
+            outp = (ctypes.c_void_p * C)(*[y_host[c].data_ptr() for c in range(C)])
+            for _ in range(2):
+                eng.process_into(inp, outp, n)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                eng.process_into(inp, outp, n)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e = {"value": n * steps / float(dt.item()) / 1e6, "unit": "M stereo frames/s",
+                   "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4 if rank == 0 else 0,
+                   "how": "b200conv_process() on pinned host buffers, wall clock, H2D / compute / D2H pipelined on separate streams"}
+        res = {
+            "value": value, "ms_per_step": ms_per_step, "launches": int(launches), "clocks": clocks, "e2e": e2e,
+            "config": {"workload": wl["desc"], "channels": C, "ir_taps": eng.ir_len(0), "block": block, "partitions": P,
+                       "blocks_per_step": T, "frames_per_step": n, "launch_groups_per_step": groups,
+                       "parallelism": "single GPU" if world == 1 else
+                       f"partition-range shards x{world} ({Ploc} partitions on rank 0) + NCCL reduce of partial spectra to rank 0",
+                       "l2": "flushed between timed steps (256 MB write)", "init_s": round(t_init, 4)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
+                         "kernel": "k_cmac_batch2 (FDL sweep)", "launch_ms": per_launch_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "note": "algorithmic bytes = SURVEY 8d figure (every block streams H and the FDL once); the batched "
+                                 "sweep reuses each H[p][k] for 16 blocks from registers, so frac > 1 is expected here and the "
+                                 "binding limit is FP32 FMA issue (see fp32); traffic = ncu dram bytes of one launch (profiles/)",
+                         "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops": fp32_peak, "frac": fp32_tflops / fp32_peak,
+                                  "peak_source": "148 SM x 128 FMA lanes/clk x 2 flop x 1965 MHz (clocks.max.sm)"},
+                         "step_share": {"cmac_ms": cm_ms / reps, "fft_ms": fft_ms / reps, "ifft_ms": ifft_ms / reps}},
+        }
+        eng.close()
+        del x_dev, y_dev
+        torch.cuda.empty_cache()
+        return res
+
+    WL0 = wl
+    T = args.blocks or (7104 if args.workload != "ir120" else 2368)
+    main_res = run_workload(wl, T, args.steps, with_e2e=not args.no_e2e, with_clocks=True)
+    extra = None
+    if args.also_ir120 and args.workload == "metric":
+        r = run_workload(dict(WORKLOADS["ir120"]), 2368, max(2, min(3, args.steps)), with_e2e=False, with_clocks=False)
+        extra = {"value": r["value"], "unit": "M stereo frames/s", "ms_per_step": r["ms_per_step"], "config": r["config"],
+                 "roofline_frac": r["roofline"]["frac"], "fp32_frac": r["roofline"]["fp32"]["frac"]}
 
     if args.sweep and rank == 0 and world == 1:
-        for v in (1, 2, 11, 12, 21, 22, 23, 25, 26):
-            e2 = Engine(C, device=local, max_batch_blocks=T + 1, cmac_variant=v)
-            e2.init_uniform(block, irs)
-            e2.set_timing(True)
-            best = 1e9
-            for _ in range(3):
-                e2.process_device(x_dev.data_ptr(), n, y_dev.data_ptr(), n, n, sync=True)
-                best = min(best, e2.last_timing()["cmac_ms"])
-            print(f"[sweep] variant {v}: cmac {best:.3f} ms  -> {n / best / 1e3:.1f} M frames/s (cmac only)", file=sys.stderr)
-            e2.close()
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--blocks", str(T)], stdout=sys.stderr)
 
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
             cpu = cpu_reference_run(wl, seconds_target=12.0, threads=os.cpu_count() or 1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "parallel_ms_per_block")}
+        C = wl["C"]
         line = {
             "metric": "stereo partitioned-convolution throughput (IR 10 s @ 48 kHz, block 512)" if args.workload == "metric"
                       else f"partitioned-convolution throughput ({wl['desc']})",
-            "value": value, "unit": "M stereo frames/s" if C == 2 else f"M {C}-channel frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "value": main_res["value"], "unit": "M stereo frames/s" if C == 2 else f"M {C}-channel frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "channels": C, "ir_taps": eng.ir_len(0), "block": block, "partitions": P,
-                       "blocks_per_step": T, "frames_per_step": n,
-                       "parallelism": "single GPU" if world == 1 else f"partition-range shards x{world} + NCCL reduce of partial spectra",
-                       "l2": "flushed between timed steps (256 MB write)", "init_s": round(t_init, 4)},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": None,
-                         "kernel": "k_cmac_batch", "launch_ms": per_launch_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes_launch,
-                         "note": "algorithmic bytes assume every block streams H and the FDL once (SURVEY §8d); the batched "
-                                 "kernel reuses each H[p][k] for 16 blocks from registers, so frac > 1 is expected and the "
-                                 "binding limit is FP32 FMA issue (see fp32)",
-                         "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
-                                  "frac": fp32_tflops / (148 * 128 * 2 * 1.965e9 / 1e12),
-                                  "peak_source": "148 SM x 128 FFMA/clk x 2 x 1965 MHz (clocks.max.sm)"},
-                         "step_share": {"cmac_ms": cm_ms / reps, "fft_ms": fft_ms / reps, "ifft_ms": ifft_ms / reps}},
-            "cpu_baseline": cpu,
+            "config": main_res["config"], "clocks": main_res["clocks"], "e2e": main_res["e2e"],
+            "gpu_launches": main_res["launches"], "roofline": main_res["roofline"], "cpu_baseline": cpu,
         }
+        if extra:
+            line["ir120"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

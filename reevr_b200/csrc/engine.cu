@@ -186,7 +186,8 @@ FftGeom fft_geometry(int M, int nblocks, int C) {
     g.warp = false; g.tws = (M <= 4096);
   }
   g.grid = dim3((nblocks + g.block.y - 1) / g.block.y, C, 1);
-  g.smem = ((g.tws ? 2 * (size_t)M : 0) + (size_t)g.block.y * 2 * M) * sizeof(float2);
+  const size_t tl = g.tws ? (((size_t)pc::tw_table_len(M) + 15) & ~(size_t)15) : 0;
+  g.smem = (tl + (size_t)g.block.y * 2 * std::max(M, 16)) * sizeof(float2);
   return g;
 }
 
@@ -375,12 +376,22 @@ int build_stage(b200conv* h, Stage& s, const float* const* ir, const std::vector
   s.Prows = round_up(std::max(s.P, 1), kPadP) + kDPre;
   s.hist = s.p_begin + round_up(std::max(s.P, 1), kPadP) + kDPre;
 
-  // twiddles exp(-2*pi*i*j/N), N = 2B, computed in double
-  const int N = 2 * B;
+  // twiddle table (layout: kernels.cuh tw_pass_offset), computed in double
+  const int N = pc::tw_table_len(B);
   std::vector<float2> tw(N);
-  for (int j = 0; j < N; ++j) {
-    const double a = -2.0 * M_PI * (double)j / (double)N;
-    tw[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+  for (int k = 0; k <= B / 2; ++k) {                       // split twiddles exp(-2*pi*i*k/(2B))
+    const double a = -2.0 * M_PI * (double)k / (2.0 * (double)B);
+    tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  for (int p = 1; p < B;) {                                // pass twiddles exp(-2*pi*i*r*k/(p*R))
+    const int R = pc::pass_radix(B, p);
+    const int off = pc::tw_pass_offset(B, p);
+    for (int r = 1; r < R; ++r)
+      for (int k = 0; k < p; ++k) {
+        const double a = -2.0 * M_PI * (double)r * (double)k / ((double)p * (double)R);
+        tw[off + (r - 1) * p + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    p *= R;
   }
   CU_CHECK(h, cudaMalloc(&s.tw, N * sizeof(float2)));
   CU_CHECK(h, cudaMemcpyAsync(s.tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice, h->s_main));

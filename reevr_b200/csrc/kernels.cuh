@@ -68,37 +68,71 @@ PC_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
 }
 
 // ------------------------------------------------------------------------------------------
-// One Stockham autosort pass, out of place (in -> out), butterfly i in [0, M/R).
-// tw = exp(-2*pi*i*j/(2M)), j < 2M (full circle of the REAL transform size N = 2M).
-//   k = i mod p ; inputs in[i + r*M/R] * w^(r*k), w = exp(-2*pi*i/(p*R)) ; outputs out[(i-k)*R + k + m*p]
+// Shared-memory addressing and twiddle-table layout of the FFT kernels.
+//
+// swz(): bank swizzle of the M-element work buffers.  Every index keeps its aligned 16-element
+// group (so contiguous accesses stay conflict-free); the low 4 bits are XOR-ed with bits 4..6 so
+// that the strided Stockham stores of the radix-8 passes (stride 8 in pass 1, 8 contiguous
+// elements every 64 in pass 2) hit 16 distinct 8-byte banks per half-warp.
+//
+// Twiddle table (device array `tw`, 3M/2 float2, built in double on the host):
+//   [0, M/2]                          split twiddles  exp(-2*pi*i*k/(2M))
+//   [tw_pass_offset(M,p) + (r-1)*p+k] pass twiddles   exp(-2*pi*i*r*k/(p*R)), k < p, r = 1..R-1
+// i.e. for a given pass and r the k-index is contiguous, which makes the reads of consecutive
+// lanes consecutive words (the sum of (R-1)*p over the earlier passes telescopes to p-1).
 // ------------------------------------------------------------------------------------------
-template <bool INV>
-PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, int M, int p, int R, int i) {
+PC_HD int swz(int a) { return a ^ ((a >> 4) & 7) ^ (((a >> 6) & 1) << 3); }
+PC_HD int tw_pass_offset(int M, int p) { return M / 2 + 1 + (p - 1); }
+PC_HD int tw_table_len(int M) { return M / 2 + 1 + (M - 1); }
+
+struct SmemIn {
+  const float2* buf;
+  PC_HD float2 operator()(int idx) const { return buf[swz(idx)]; }
+};
+struct SmemOut {
+  float2* buf;
+  PC_HD void operator()(int idx, float2 v) const { buf[swz(idx)] = v; }
+};
+// forward first pass reads the time-domain block straight from global memory:
+// z[n] = x[2n] + i*x[2n+1], zero beyond the nv valid samples (the [x ; 0] padding is never stored)
+struct FwdGlobalIn {
+  const float* src; int nv;
+  PC_HD float2 operator()(int n) const {
+    const int i0 = 2 * n, i1 = 2 * n + 1;
+    return make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// One Stockham autosort pass (radix R, sub-transform length p -> p*R), butterfly i in [0, M/R):
+//   k = i mod p ; inputs in(i + r*M/R) * w^(r*k) ; outputs out((i-k)*R + k + m*p) = DFT_R[m]
+// `in` / `out` are accessor functors so the first / last pass can touch global memory directly.
+// ------------------------------------------------------------------------------------------
+template <bool INV, class In, class Out>
+PC_HD void stockham_butterfly(In in, Out out, const float2* twp, int M, int p, int R, int i) {
   const int k = i & (p - 1);
   const int j = (i - k) * R + k;
   const int stride = M / R;
-  const int tstep = (2 * M) / (p * R);          // table step for exp(-2*pi*i*k/(p*R))
   if (R == 8) {
     float2 a[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = in[i + r * stride];
+    for (int r = 0; r < 8; ++r) a[r] = in(i + r * stride);
     if (k != 0) {
 #pragma unroll
       for (int r = 1; r < 8; ++r) {
-        float2 w = tw[r * k * tstep];
+        float2 w = twp[(r - 1) * p + k];
         if (INV) w.y = -w.y;
         a[r] = c_mul(a[r], w);
       }
     }
-    // radix-2 stage on (r, r+4), then W8 twiddles on the odd half, then two DFT4
+    // radix-2 stage on (r, r+4), W8 twiddles on the odd half, then two DFT4
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float2 s = c_add(a[r], a[r + 4]), d = c_sub(a[r], a[r + 4]);
       a[r] = s; a[r + 4] = d;
     }
     const float h = 0.70710678118654752440f;
-    // a5 *= W8^1, a6 *= W8^2, a7 *= W8^3   (forward W8 = e^{-i*pi/4}; inverse conjugate)
-    if (!INV) {
+    if (!INV) {   // W8 = e^{-i*pi/4}
       a[5] = make_float2(h * (a[5].x + a[5].y), h * (a[5].y - a[5].x));
       a[6] = make_float2(a[6].y, -a[6].x);
       a[7] = make_float2(h * (a[7].y - a[7].x), -h * (a[7].x + a[7].y));
@@ -111,34 +145,27 @@ PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, i
     dft4<INV>(a[4], a[5], a[6], a[7]);     // odd outputs  X[1], X[3], X[5], X[7]
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      out[j + (2 * m) * p] = a[m];
-      out[j + (2 * m + 1) * p] = a[4 + m];
+      out(j + (2 * m) * p, a[m]);
+      out(j + (2 * m + 1) * p, a[4 + m]);
     }
   } else if (R == 4) {
-    float2 a0 = in[i];
-    float2 a1 = in[i + stride];
-    float2 a2 = in[i + 2 * stride];
-    float2 a3 = in[i + 3 * stride];
+    float2 a0 = in(i), a1 = in(i + stride), a2 = in(i + 2 * stride), a3 = in(i + 3 * stride);
     if (k != 0) {
-      float2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
+      float2 w1 = twp[k], w2 = twp[p + k], w3 = twp[2 * p + k];
       if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       a1 = c_mul(a1, w1); a2 = c_mul(a2, w2); a3 = c_mul(a3, w3);
     }
     dft4<INV>(a0, a1, a2, a3);
-    out[j] = a0;
-    out[j + p] = a1;
-    out[j + 2 * p] = a2;
-    out[j + 3 * p] = a3;
+    out(j, a0); out(j + p, a1); out(j + 2 * p, a2); out(j + 3 * p, a3);
   } else {
-    float2 a0 = in[i];
-    float2 a1 = in[i + stride];
+    float2 a0 = in(i), a1 = in(i + stride);
     if (k != 0) {
-      float2 w1 = tw[k * tstep];
+      float2 w1 = twp[k];
       if (INV) w1.y = -w1.y;
       a1 = c_mul(a1, w1);
     }
-    out[j] = c_add(a0, a1);
-    out[j + p] = c_sub(a0, a1);
+    out(j, c_add(a0, a1));
+    out(j + p, c_sub(a0, a1));
   }
 }
 
@@ -146,21 +173,20 @@ PC_HD void stockham_butterfly(const float2* in, float2* out, const float2* tw, i
 // K1 phases.  Real transform of size N = 2M computed as an M-point complex transform of
 // z[n] = x[2n] + i*x[2n+1] followed by the even/odd split.
 // ------------------------------------------------------------------------------------------
-// load: src = first sample of this block, nv = valid samples (<= M = B), rest is zero padding
+// load (only used when M == 1, i.e. no pass exists): z -> work buffer
 PC_HD void fwd_load(const float* src, int nv, float2* z, int M, int n) {
-  const int i0 = 2 * n, i1 = 2 * n + 1;
-  z[n] = make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
+  z[swz(n)] = FwdGlobalIn{src, nv}(n);
 }
 
-// split: Z = FFT_M(z) -> packed spectrum row X (B = M entries), k in [0, M/2]
+// split: Z = FFT_M(z) (swizzled work buffer) -> packed spectrum row X (B = M entries), k in [0, M/2]
 PC_HD void fwd_split(const float2* Z, float2* X, const float2* tw, int M, int k) {
   if (k == 0) {
-    const float2 z0 = Z[0];
+    const float2 z0 = Z[swz(0)];
     X[0] = make_float2(z0.x + z0.y, z0.x - z0.y);      // (DC, Nyquist)
     return;
   }
-  const float2 a = Z[k];
-  const float2 b = c_conj(Z[M - k]);
+  const float2 a = Z[swz(k)];
+  const float2 b = c_conj(Z[swz(M - k)]);
   const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
   const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
   const float2 O = make_float2(D.y, -D.x);              // -i * D
@@ -187,7 +213,7 @@ PC_HD float2 ola_merge(const float2* Yt, const float2* Yp, int M, int k) {
 PC_HD void inv_pre(const float2* Yt, const float2* Yp, float2* Z, const float2* tw, int M, int k) {
   if (k == 0) {
     const float2 w0 = ola_merge(Yt, Yp, M, 0);
-    Z[0] = make_float2(0.5f * (w0.x + w0.y), 0.5f * (w0.x - w0.y));
+    Z[swz(0)] = make_float2(0.5f * (w0.x + w0.y), 0.5f * (w0.x - w0.y));
     return;
   }
   const float2 a = ola_merge(Yt, Yp, M, k);
@@ -195,8 +221,8 @@ PC_HD void inv_pre(const float2* Yt, const float2* Yp, float2* Z, const float2* 
   const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
   const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
   const float2 O = c_mul(c_conj(tw[k]), D);
-  Z[k] = make_float2(E.x - O.y, E.y + O.x);
-  Z[M - k] = make_float2(E.x + O.y, O.x - E.y);
+  Z[swz(k)] = make_float2(E.x - O.y, E.y + O.x);
+  Z[swz(M - k)] = make_float2(E.x + O.y, O.x - E.y);
 }
 
 // where the B output samples of one block go
@@ -212,16 +238,32 @@ struct OutSpec {
   long long abs0;        // absolute stream position of sample 0 (ring read position)
 };
 
-PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int s) {
+PC_HD void inv_store_sample(float val, float scale, const OutSpec& o, int s) {
   const long long idx = o.index0 + s;
   if (idx < o.lo || idx >= o.hi) return;
-  const float2 v = z[s >> 1];
-  float r = ((s & 1) ? v.y : v.x) * scale;
+  float r = val * scale;
 #pragma unroll
   for (int a = 0; a < 3; ++a)
     if (a < o.n_add) r += o.add[a][(o.abs0 + s) & o.add_mask[a]];
   o.dst[idx & o.mask] = r;
 }
+
+// sample s of the block from the (swizzled) work buffer; used when M == 1 (no pass)
+PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int s) {
+  const float2 v = z[swz(s >> 1)];
+  inv_store_sample((s & 1) ? v.y : v.x, scale, o, s);
+}
+
+// last inverse pass writes z[n] = (x[2n], x[2n+1]) straight to the destination; only the first
+// B = M output samples (n < M/2) of the 2M-point inverse transform are needed
+struct InvGlobalOut {
+  const OutSpec* o; float scale; int half;
+  PC_HD void operator()(int n, float2 v) const {
+    if (n >= half) return;
+    inv_store_sample(v.x, scale, *o, 2 * n);
+    inv_store_sample(v.y, scale, *o, 2 * n + 1);
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // K2: per-thread body of the batched FDL sweep.
@@ -481,29 +523,42 @@ __global__ void k_fwd_fft(FwdParams P) {
   const float2* tw = P.tw;
   float2* data = pc_smem;
   if (TWS) {
+    const int tl = tw_table_len(M);
     const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
-    for (int j = tid; j < 2 * M; j += nthr) pc_smem[j] = P.tw[j];
+    for (int j = tid; j < tl; j += nthr) pc_smem[j] = P.tw[j];
     tw = pc_smem;
-    data = pc_smem + 2 * M;
+    data = pc_smem + ((tl + 15) & ~15);
+    __syncthreads();
   }
   float2* bufA = data + (size_t)threadIdx.y * 2 * M;
   float2* bufB = bufA + M;
+  int nv = 0;
+  const float* src = nullptr;
   if (active) {
     const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
     long long rem = nv_total - (long long)blk * M;
-    const int nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
-    const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
-    for (int n = tx; n < M; n += nth) fwd_load(src, nv, bufA, M, n);
+    nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
+    src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
   }
-  __syncthreads();                      // twiddles staged, transform loaded
   float2* in = bufA; float2* out = bufB;
-  for (int p = 1; p < M;) {
-    const int R = pass_radix(M, p);
+  if (M == 1) {
+    if (active && tx == 0) fwd_load(src, nv, in, M, 0);
+  } else {
+    // first pass straight from global memory (zero padding applied in the accessor)
+    const int R0 = pass_radix(M, 1);
     if (active)
-      for (int i = tx; i < M / R; i += nth) stockham_butterfly<false>(in, out, tw, M, p, R, i);
+      for (int i = tx; i < M / R0; i += nth)
+        stockham_butterfly<false>(FwdGlobalIn{src, nv}, SmemOut{in}, tw + tw_pass_offset(M, 1), M, 1, R0, i);
     fft_sync<WARP>();
-    float2* t = in; in = out; out = t;
-    p *= R;
+    for (int p = R0; p < M;) {
+      const int R = pass_radix(M, p);
+      if (active)
+        for (int i = tx; i < M / R; i += nth)
+          stockham_butterfly<false>(SmemIn{in}, SmemOut{out}, tw + tw_pass_offset(M, p), M, p, R, i);
+      fft_sync<WARP>();
+      float2* t = in; in = out; out = t;
+      p *= R;
+    }
   }
   if (active) {
     float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
@@ -543,41 +598,52 @@ __global__ void k_inv_fft_ola(InvParams P) {
   const float2* tw = P.tw;
   float2* data = pc_smem;
   if (TWS) {
+    const int tl = tw_table_len(M);
     const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
-    for (int j = tid; j < 2 * M; j += nthr) pc_smem[j] = P.tw[j];
+    for (int j = tid; j < tl; j += nthr) pc_smem[j] = P.tw[j];
     tw = pc_smem;
-    data = pc_smem + 2 * M;
+    data = pc_smem + ((tl + 15) & ~15);
     __syncthreads();                    // inv_pre already needs the table
   }
   float2* bufA = data + (size_t)threadIdx.y * 2 * M;
   float2* bufB = bufA + M;
+  OutSpec o;
   if (active) {
+    o.dst = P.dst + (long long)c * P.dst_cstride;
+    o.index0 = P.index0 + (long long)blk * M;
+    o.lo = P.lo; o.hi = P.hi; o.mask = P.mask;
+    o.n_add = P.n_add;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      o.add[a] = a < P.n_add ? P.add[a] + (long long)c * P.add_cstride[a] : nullptr;
+      o.add_mask[a] = P.add_mask[a];
+    }
+    o.abs0 = P.abs0 + (long long)blk * M;
     const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
     const float2* Yp = Yt - P.y_rstride;
     for (int k = tx; k <= M / 2; k += nth) inv_pre(Yt, Yp, bufA, tw, M, k);
   }
   fft_sync<WARP>();
   float2* in = bufA; float2* out = bufB;
-  for (int p = 1; p < M;) {
-    const int R = pass_radix(M, p);
-    if (active)
-      for (int i = tx; i < M / R; i += nth) stockham_butterfly<true>(in, out, tw, M, p, R, i);
-    fft_sync<WARP>();
-    float2* t = in; in = out; out = t;
-    p *= R;
-  }
-  if (active) {
-    OutSpec o;
-    o.dst = P.dst + (long long)c * P.dst_cstride;
-    o.index0 = P.index0 + (long long)blk * M;
-    o.lo = P.lo; o.hi = P.hi; o.mask = P.mask;
-    o.n_add = P.n_add;
-    for (int a = 0; a < 3; ++a) {
-      o.add[a] = a < P.n_add ? P.add[a] + (long long)c * P.add_cstride[a] : nullptr;
-      o.add_mask[a] = P.add_mask[a];
+  if (M == 1) {
+    if (active && tx == 0) inv_store(in, M, P.scale, o, 0);
+  } else {
+    for (int p = 1; p < M;) {
+      const int R = pass_radix(M, p);
+      const bool last = p * R == M;
+      if (active) {
+        if (!last) {
+          for (int i = tx; i < M / R; i += nth)
+            stockham_butterfly<true>(SmemIn{in}, SmemOut{out}, tw + tw_pass_offset(M, p), M, p, R, i);
+        } else {      // last pass: scaled samples straight to the destination (first half only)
+          for (int i = tx; i < M / R; i += nth)
+            stockham_butterfly<true>(SmemIn{in}, InvGlobalOut{&o, P.scale, M / 2}, tw + tw_pass_offset(M, p), M, p, R, i);
+        }
+      }
+      if (!last) fft_sync<WARP>();
+      float2* t = in; in = out; out = t;
+      p *= R;
     }
-    o.abs0 = P.abs0 + (long long)blk * M;
-    for (int s = tx; s < M; s += nth) inv_store(in, M, P.scale, o, s);
   }
 }
 
@@ -651,8 +717,9 @@ struct EmuDim { int x, y, z; };
 
 inline void emu_fwd_fft(EmuDim grid, EmuDim block, const FwdParams& P) {
   const int M = P.M;
-  float2* bufA = new float2[(size_t)M];
-  float2* bufB = new float2[(size_t)M];
+  const int Mp = M < 16 ? 16 : M;
+  float2* bufA = new float2[(size_t)Mp];
+  float2* bufB = new float2[(size_t)Mp];
   for (int c = 0; c < grid.y; ++c)
     for (int bx = 0; bx < grid.x; ++bx)
       for (int ty = 0; ty < block.y; ++ty) {
@@ -662,13 +729,20 @@ inline void emu_fwd_fft(EmuDim grid, EmuDim block, const FwdParams& P) {
         long long rem = nv_total - (long long)blk * M;
         const int nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
         const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
-        for (int n = 0; n < M; ++n) fwd_load(src, nv, bufA, M, n);
         float2* in = bufA; float2* out = bufB;
-        for (int p = 1; p < M;) {
-          const int R = pass_radix(M, p);
-          for (int i = 0; i < M / R; ++i) stockham_butterfly<false>(in, out, P.tw, M, p, R, i);
-          float2* t = in; in = out; out = t;
-          p *= R;
+        if (M == 1) {
+          fwd_load(src, nv, in, M, 0);
+        } else {
+          const int R0 = pass_radix(M, 1);
+          for (int i = 0; i < M / R0; ++i)
+            stockham_butterfly<false>(FwdGlobalIn{src, nv}, SmemOut{in}, P.tw + tw_pass_offset(M, 1), M, 1, R0, i);
+          for (int p = R0; p < M;) {
+            const int R = pass_radix(M, p);
+            for (int i = 0; i < M / R; ++i)
+              stockham_butterfly<false>(SmemIn{in}, SmemOut{out}, P.tw + tw_pass_offset(M, p), M, p, R, i);
+            float2* t = in; in = out; out = t;
+            p *= R;
+          }
         }
         float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
         for (int k = 0; k <= M / 2; ++k) fwd_split(in, X, P.tw, M, k);
@@ -718,23 +792,14 @@ inline void emu_cmac_batch2(EmuDim grid, const CmacParams& P) {
 
 inline void emu_inv_fft_ola(EmuDim grid, EmuDim block, const InvParams& P) {
   const int M = P.M;
-  float2* bufA = new float2[(size_t)M];
-  float2* bufB = new float2[(size_t)M];
+  const int Mp = M < 16 ? 16 : M;
+  float2* bufA = new float2[(size_t)Mp];
+  float2* bufB = new float2[(size_t)Mp];
   for (int c = 0; c < grid.y; ++c)
     for (int bx = 0; bx < grid.x; ++bx)
       for (int ty = 0; ty < block.y; ++ty) {
         const int blk = bx * block.y + ty;
         if (blk >= P.nblocks) continue;
-        const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
-        const float2* Yp = Yt - P.y_rstride;
-        for (int k = 0; k <= M / 2; ++k) inv_pre(Yt, Yp, bufA, P.tw, M, k);
-        float2* in = bufA; float2* out = bufB;
-        for (int p = 1; p < M;) {
-          const int R = pass_radix(M, p);
-          for (int i = 0; i < M / R; ++i) stockham_butterfly<true>(in, out, P.tw, M, p, R, i);
-          float2* t = in; in = out; out = t;
-          p *= R;
-        }
         OutSpec o;
         o.dst = P.dst + (long long)c * P.dst_cstride;
         o.index0 = P.index0 + (long long)blk * M;
@@ -745,7 +810,24 @@ inline void emu_inv_fft_ola(EmuDim grid, EmuDim block, const InvParams& P) {
           o.add_mask[a] = P.add_mask[a];
         }
         o.abs0 = P.abs0 + (long long)blk * M;
-        for (int sidx = 0; sidx < M; ++sidx) inv_store(in, M, P.scale, o, sidx);
+        const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
+        const float2* Yp = Yt - P.y_rstride;
+        for (int k = 0; k <= M / 2; ++k) inv_pre(Yt, Yp, bufA, P.tw, M, k);
+        float2* in = bufA; float2* out = bufB;
+        if (M == 1) {
+          inv_store(in, M, P.scale, o, 0);
+        } else {
+          for (int p = 1; p < M;) {
+            const int R = pass_radix(M, p);
+            const bool last = p * R == M;
+            for (int i = 0; i < M / R; ++i) {
+              if (!last) stockham_butterfly<true>(SmemIn{in}, SmemOut{out}, P.tw + tw_pass_offset(M, p), M, p, R, i);
+              else stockham_butterfly<true>(SmemIn{in}, InvGlobalOut{&o, P.scale, M / 2}, P.tw + tw_pass_offset(M, p), M, p, R, i);
+            }
+            float2* t = in; in = out; out = t;
+            p *= R;
+          }
+        }
       }
   delete[] bufA; delete[] bufB;
 }

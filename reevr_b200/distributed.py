@@ -31,11 +31,16 @@ def attach_reduce(engine, device: int | None = None, group=None, root: int = 0) 
     backend = dist.get_backend(group)
     if backend == "nccl":
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        stream = torch.cuda.ExternalStream(engine.stream, device=dev)
+        streams = {}
 
-        def hook(ptr: int, n: int, _stream: int) -> int:
+        def hook(ptr: int, n: int, stream_ptr: int) -> int:
+            # the engine hands over the stream the partial spectra were produced on (its post stream):
+            # the reduce is ordered after the sweep and before the inverse FFT on that stream
+            st = streams.get(stream_ptr)
+            if st is None:
+                st = streams[stream_ptr] = torch.cuda.ExternalStream(stream_ptr, device=dev)
             t = torch.as_tensor(_CudaView(ptr, n), device=dev)
-            with torch.cuda.stream(stream):          # ordered after the sweep, before the inverse FFT
+            with torch.cuda.stream(st):
                 dist.reduce(t, dst=root, op=dist.ReduceOp.SUM, group=group)
             return 0
     else:

@@ -109,7 +109,8 @@ def test_linearity_and_time_invariance_metric_shape():
     xs = [np.concatenate([np.zeros(s, np.float32), p[:-s]]) for p in x1]
     ysh = run(xs)
     for c in range(2):
-        assert np.all(ysh[c][:s] == 0)
+        assert np.all(ysh[c][:1024] == 0)           # whole blocks of silence are exactly silent
+        assert np.max(np.abs(ysh[c][1024:s])) <= TOL * np.max(np.abs(y1[c]))   # block that contains the onset: rounding only
         assert peak_err(ysh[c][s:], y1[c][:-s]) <= TOL
 
 

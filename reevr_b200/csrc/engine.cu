@@ -306,8 +306,10 @@ int launch_cmac_stream(b200conv* h, const pc::CmacParams& P, int C) {
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
   if (variant == 0) {
+    // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
+    // launch group is long enough to fill 16-block tiles, TT = 8 below that)
     if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
-    else variant = (P.nblocks >= 64) ? 1 : 3;
+    else variant = (P.nblocks >= 64) ? 22 : 26;
   }
   if (variant == 100) {
     if (P.nblocks > kStreamNBS || P.B < 2) return fail(h, B200CONV_EINVAL, "streaming sweep needs nblocks <= 4 and B >= 2");
@@ -536,6 +538,8 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
   const int C = h->C;
   const bool root = h->cfg.shard_rank == 0;
   cudaStream_t ps = overlap ? h->s_post : h->s_main;
+  if (n == 0) return 0;
+  if (n + h->stages[0].B > h->Lmax) return fail(h, B200CONV_ESTATE, "launch group larger than the staging buffers");
   // stages >= 1 first (their look-ahead output may be consumed by the head within this group)
   for (int si = (int)h->stages.size() - 1; si >= 0; --si) {
     Stage& s = h->stages[si];
@@ -815,8 +819,11 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   // throughput path: H2D / compute / D2H of successive groups overlap on three streams
   size_t done = 0;
   int i = 0;
-  // split long calls into at least 4 groups so that the copies overlap with compute
-  size_t grp = std::min(chunk, std::max((size_t)B0 * 64, (len / 4 + B0 - 1) / B0 * B0));
+  // split long calls into ~3 groups so that the PCIe copies overlap with compute; group length is a
+  // multiple of 64 blocks (= one sweep tile of 4 warps x 16 blocks) to keep the sweep grid wave-aligned
+  const size_t tile = (size_t)B0 * 64;
+  size_t grp = ((len + 2) / 3 + tile - 1) / tile * tile;
+  grp = std::min(grp, chunk >= tile ? chunk / tile * tile : chunk);
   for (; done < len; ++i) {
     const int b = i & 1;
     const size_t n = std::min(len - done, grp);

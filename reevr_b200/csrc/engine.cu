@@ -180,7 +180,8 @@ FftGeom fft_geometry(int M, int nblocks, int C) {
     int ty = std::max(1, std::min(8, 4096 / std::max(M, 1)));
     ty = std::min(ty, std::max(1, nblocks));
     g.block = dim3(32, ty, 1);
-    g.warp = true; g.tws = true;
+    g.warp = true;
+    g.tws = (long long)nblocks * C >= 64;    // real-time calls: a few transforms, table read through L1 instead
   } else {                               // whole CTA per transform
     g.block = dim3(std::min(512, M / 8), 1, 1);
     g.warp = false; g.tws = (M <= 4096);
@@ -197,7 +198,8 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
 #if defined(PC_EMULATE)
   pc::emu_fwd_fft({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  if (g.warp) pc::k_fwd_fft<true, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
+  if (g.warp && g.tws) pc::k_fwd_fft<true, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
+  else if (g.warp) pc::k_fwd_fft<true, false><<<g.grid, g.block, g.smem, h->s_main>>>(P);
   else if (g.tws) pc::k_fwd_fft<false, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
   else pc::k_fwd_fft<false, false><<<g.grid, g.block, g.smem, h->s_main>>>(P);
 #endif
@@ -213,7 +215,8 @@ int launch_inv(b200conv* h, const pc::InvParams& P, int C, cudaStream_t st) {
 #if defined(PC_EMULATE)
   pc::emu_inv_fft_ola({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  if (g.warp) pc::k_inv_fft_ola<true, true><<<g.grid, g.block, g.smem, st>>>(P);
+  if (g.warp && g.tws) pc::k_inv_fft_ola<true, true><<<g.grid, g.block, g.smem, st>>>(P);
+  else if (g.warp) pc::k_inv_fft_ola<true, false><<<g.grid, g.block, g.smem, st>>>(P);
   else if (g.tws) pc::k_inv_fft_ola<false, true><<<g.grid, g.block, g.smem, st>>>(P);
   else pc::k_inv_fft_ola<false, false><<<g.grid, g.block, g.smem, st>>>(P);
 #endif
@@ -302,14 +305,54 @@ int launch_cmac_stream(b200conv* h, const pc::CmacParams& P, int C) {
   return 0;
 }
 
+template <int NB, int U>
+void launch_stream_rows_t(b200conv* h, const pc::StreamParams& S, dim3 grid, int threads) {
+#if defined(PC_EMULATE)
+  pc::emu_cmac_stream_rows<NB, U>({(int)grid.x, (int)grid.y, (int)grid.z}, threads, S);
+#else
+  pc::k_cmac_stream_rows<NB, U><<<grid, dim3(threads, 1, 1), 0, h->s_main>>>(S);
+#endif
+}
+
+// row-walking streaming sweep (B >= 64): see k_cmac_stream_rows
+int launch_cmac_stream_rows(b200conv* h, const pc::CmacParams& P, int C) {
+  pc::StreamParams S{};
+  S.H = P.H; S.h_cstride = P.h_cstride;
+  S.X = P.X; S.x_cstride = P.x_cstride; S.xrow0 = P.xrow0;
+  S.Y = P.Y; S.y_cstride = P.y_cstride; S.y_rstride = P.y_rstride; S.yrow0 = P.yrow0;
+  S.B = P.B; S.P = P.Ppad; S.nblocks = P.nblocks;
+  const int threads = std::min(256, P.B / 2);
+  const int xt = (P.B / 2 + threads - 1) / threads;
+  // ~3 CTAs per SM, but no CTA with fewer than 8 partitions (one unrolled load batch)
+  int nsplit = std::max(1, (3 * h->n_sm) / std::max(1, xt * C));
+  nsplit = std::max(1, std::min(nsplit, std::max(1, P.Ppad / 8)));
+  S.nsplit = nsplit;
+  if (nsplit > 1)
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_main));
+  dim3 grid(xt, nsplit, C);
+  int id = timing_begin(h, kKindCmac);
+  if (P.nblocks <= 1) launch_stream_rows_t<1, 8>(h, S, grid, threads);
+  else if (P.nblocks == 2) launch_stream_rows_t<2, 4>(h, S, grid, threads);
+  else launch_stream_rows_t<4, 2>(h, S, grid, threads);
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
 // P.Ppad enters as the number of real (unpadded) partition rows of this shard
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
   if (variant == 0) {
     // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
     // launch group is long enough to fill 16-block tiles, TT = 8 below that)
-    if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
+    if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
+    else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;
+  }
+  if (variant == 101) {
+    if (P.nblocks > kStreamNBS || P.B < 4) return fail(h, B200CONV_EINVAL, "streaming sweep needs nblocks <= 4 and B >= 4");
+    return launch_cmac_stream_rows(h, P, C);
   }
   if (variant == 100) {
     if (P.nblocks > kStreamNBS || P.B < 2) return fail(h, B200CONV_EINVAL, "streaming sweep needs nblocks <= 4 and B >= 2");
@@ -545,19 +588,24 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
     Stage& s = h->stages[si];
     const int B = s.B;
     const size_t row = (size_t)C * B;           // float2 per Y row (all channels)
-    // append the new samples behind the open block's samples
-    CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
-                                  n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
     const size_t total = (size_t)s.fill + n;
     const int complete = (int)(total / B);
     const int partial = (int)(total % B);
     const int nb = (si == 0) ? complete + (partial > 0 ? 1 : 0) : complete;
+    // With an empty open block the forward FFT reads the caller's buffer directly; only a trailing
+    // partial block is buffered.  Otherwise the new samples are appended behind the open block's.
+    const bool direct = (s.fill == 0);
+    if (!direct)
+      CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                    n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
     const int yb = s.ybuf;
     float2* Yb = s.Y[yb];
     if (nb > 0) {
       if (s.head + nb + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
       pc::FwdParams fp{};
-      fp.src = s.inbuf; fp.src_cstride = (long long)s.in_stride; fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
+      fp.src = direct ? in_dev : s.inbuf;
+      fp.src_cstride = direct ? (long long)in_stride : (long long)s.in_stride;
+      fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
       fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
       fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
       if (int rc = launch_fwd(h, fp, C)) return rc;
@@ -612,14 +660,19 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
                                   cudaMemcpyDeviceToDevice, ps));
       if (overlap) CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
       s.ybuf = nxt;
-      if (partial > 0)
-        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), s.inbuf + (size_t)complete * B,
-                                      s.in_stride * sizeof(float), partial * sizeof(float), C,
-                                      cudaMemcpyDeviceToDevice, h->s_main));
+      if (partial > 0) {
+        const float* tail_src = direct ? in_dev + (size_t)complete * B : s.inbuf + (size_t)complete * B;
+        const size_t tail_pitch = direct ? in_stride : s.in_stride;
+        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), tail_src, tail_pitch * sizeof(float),
+                                      partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+      }
       s.head += complete;
       s.blocks_done += complete;
-    } else if (overlap && nb > 0) {
-      CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
+    } else {
+      if (direct && partial > 0)     // nothing completed: keep the partial block's samples for the next call
+        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                      partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+      if (overlap && nb > 0) CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
     }
     s.fill = partial;
   }
@@ -689,6 +742,8 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
     // the FFT kernels need up to 192 KB of dynamic shared memory (B = 4096: table + ping-pong buffers)
     const int kSmem = 200 * 1024;
     ok = cudaFuncSetAttribute(pc::k_fwd_fft<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;

@@ -440,6 +440,60 @@ PC_HD void cmac_stream_thread(const float2* __restrict__ Hk,   // &H[c][0][k2]
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K2s (row form): streaming sweep where a CTA walks whole spectrum rows.  Thread = two adjacent
+// bins (one 16-byte load per operand), CTA = `threads` consecutive bin pairs of ONE row, CTAs
+// split the partition range [0, P) in contiguous slices; no cross-warp reduction, each thread adds
+// its NB results to Y with RED.ADD (or stores them when the slice is the whole range).
+// U partitions are loaded back to back before any arithmetic: U*(1+NB) independent 16-byte loads
+// in flight per thread — this is what makes the kernel bandwidth- instead of latency-bound.
+// ------------------------------------------------------------------------------------------
+template <int NB, int U>
+PC_HD void cmac_stream_rows(const float2* __restrict__ Hk, const float2* __restrict__ Xk, long long rowstride,
+                            int p_lo, int p_hi, bool packed_first, float2* acc /*[NB][2]*/) {
+#pragma unroll
+  for (int i = 0; i < 2 * NB; ++i) acc[i] = make_float2(0.f, 0.f);
+  const float m = packed_first ? 0.0f : 1.0f;
+  int p = p_lo;
+  for (; p + U <= p_hi; p += U) {
+    float4c h[U], x[U][NB];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      h[u] = ld_pair(Hk + (long long)(p + u) * rowstride);
+#pragma unroll
+      for (int t = 0; t < NB; ++t) x[u][t] = ld_pair(Xk + (long long)(t - p - u) * rowstride);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        float re = fmaf(h[u].a.x, x[u][t].a.x, acc[2 * t].x);
+        re = fmaf(-m * h[u].a.y, x[u][t].a.y, re);
+        const float im = packed_first ? fmaf(h[u].a.y, x[u][t].a.y, acc[2 * t].y)
+                                      : fmaf(h[u].a.y, x[u][t].a.x, fmaf(h[u].a.x, x[u][t].a.y, acc[2 * t].y));
+        acc[2 * t] = make_float2(re, im);
+        acc[2 * t + 1].x = fmaf(-h[u].b.y, x[u][t].b.y, fmaf(h[u].b.x, x[u][t].b.x, acc[2 * t + 1].x));
+        acc[2 * t + 1].y = fmaf(h[u].b.y, x[u][t].b.x, fmaf(h[u].b.x, x[u][t].b.y, acc[2 * t + 1].y));
+      }
+    }
+  }
+  for (; p < p_hi; ++p) {
+    const float4c h = ld_pair(Hk + (long long)p * rowstride);
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      const float4c x = ld_pair(Xk + (long long)(t - p) * rowstride);
+      float re = fmaf(h.a.x, x.a.x, acc[2 * t].x);
+      re = fmaf(-m * h.a.y, x.a.y, re);
+      const float im = packed_first ? fmaf(h.a.y, x.a.y, acc[2 * t].y)
+                                    : fmaf(h.a.y, x.a.x, fmaf(h.a.x, x.a.y, acc[2 * t].y));
+      acc[2 * t] = make_float2(re, im);
+      acc[2 * t + 1].x = fmaf(-h.b.y, x.b.y, fmaf(h.b.x, x.b.x, acc[2 * t + 1].x));
+      acc[2 * t + 1].y = fmaf(h.b.y, x.b.x, fmaf(h.b.x, x.b.y, acc[2 * t + 1].y));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // launch parameter blocks (shared by the CUDA kernels and the CPU emulation drivers)
 // ------------------------------------------------------------------------------------------
@@ -664,6 +718,34 @@ __global__ void __launch_bounds__(32 * TW, MINB) k_cmac_batch2(CmacParams P) {
     if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
 }
 
+// grid (ceil(B/2/threads), nsplit, C), block (threads) with threads = min(256, B/2)
+template <int NB, int U>
+__global__ void __launch_bounds__(256) k_cmac_stream_rows(StreamParams P) {
+  const int k2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int c = blockIdx.z;
+  if (k2 >= P.B) return;
+  const int per = (P.P + P.nsplit - 1) / P.nsplit;
+  const int p_lo = blockIdx.y * per;
+  const int p_hi = min(P.P, p_lo + per);
+  if (p_lo >= p_hi && P.nsplit > 1) return;
+  const float2* Hk = P.H + (long long)c * P.h_cstride + k2;
+  const float2* Xk = P.X + (long long)c * P.x_cstride + P.xrow0 * (long long)P.B + k2;
+  float2 acc[2 * NB];
+  cmac_stream_rows<NB, U>(Hk, Xk, P.B, p_lo, p_hi, k2 == 0, acc);
+#pragma unroll
+  for (int t = 0; t < NB; ++t) {
+    if (t < P.nblocks) {
+      float* y = reinterpret_cast<float*>(P.Y + (long long)c * P.y_cstride + (P.yrow0 + t) * P.y_rstride + k2);
+      if (P.nsplit == 1) {
+        *reinterpret_cast<float4*>(y) = make_float4(acc[2 * t].x, acc[2 * t].y, acc[2 * t + 1].x, acc[2 * t + 1].y);
+      } else {
+        atomicAdd(y + 0, acc[2 * t].x); atomicAdd(y + 1, acc[2 * t].y);
+        atomicAdd(y + 2, acc[2 * t + 1].x); atomicAdd(y + 3, acc[2 * t + 1].y);
+      }
+    }
+  }
+}
+
 // grid (B/64 or 1, nsplit, C), block (32, PW); smem: PW * NBS * 32 * 4 floats (static)
 template <int NBS, int PW>
 __global__ void __launch_bounds__(32 * PW) k_cmac_stream(StreamParams P) {
@@ -859,6 +941,30 @@ inline void emu_cmac_stream(EmuDim grid, const StreamParams& P) {
           }
         }
       }
+}
+
+template <int NB, int U>
+inline void emu_cmac_stream_rows(EmuDim grid, int threads, const StreamParams& P) {
+  for (int c = 0; c < grid.z; ++c)
+    for (int by = 0; by < grid.y; ++by)
+      for (int bx = 0; bx < grid.x; ++bx)
+        for (int tid = 0; tid < threads; ++tid) {
+          const int k2 = (bx * threads + tid) * 2;
+          if (k2 >= P.B) continue;
+          const int per = (P.P + P.nsplit - 1) / P.nsplit;
+          const int p_lo = by * per;
+          const int p_hi = P.P < p_lo + per ? P.P : p_lo + per;
+          if (p_lo >= p_hi && P.nsplit > 1) continue;
+          const float2* Hk = P.H + (long long)c * P.h_cstride + k2;
+          const float2* Xk = P.X + (long long)c * P.x_cstride + P.xrow0 * (long long)P.B + k2;
+          float2 acc[2 * NB];
+          cmac_stream_rows<NB, U>(Hk, Xk, P.B, p_lo, p_hi, k2 == 0, acc);
+          for (int t = 0; t < NB && t < P.nblocks; ++t) {
+            float2* y = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t) * P.y_rstride + k2;
+            if (P.nsplit == 1) { y[0] = acc[2 * t]; y[1] = acc[2 * t + 1]; }
+            else { y[0].x += acc[2 * t].x; y[0].y += acc[2 * t].y; y[1].x += acc[2 * t + 1].x; y[1].y += acc[2 * t + 1].y; }
+          }
+        }
 }
 #endif  // !__CUDACC__
 

@@ -171,26 +171,49 @@ void timing_collect(b200conv* h) {
 }
 
 // ---- kernel launchers ----------------------------------------------------------------------
-// block (tx, ty): tx threads per transform, ty transforms per CTA; see k_fwd_fft
-struct FftGeom { dim3 grid, block; size_t smem; bool warp, tws; };
+// block (NT, ty): NT threads per transform, ty transforms per CTA; see k_fwd_fft
+struct FftGeom { dim3 grid, block; size_t smem; bool tws; };
 
 FftGeom fft_geometry(int M, int nblocks, int C) {
   FftGeom g;
-  if (M <= 1024) {                       // one warp per transform
-    int ty = std::max(1, std::min(8, 4096 / std::max(M, 1)));
+  const int nt = pc::fft_threads(M);
+  int ty = 1;
+  if (pc::fft_warp_mode(M)) {            // one warp per transform
+    ty = std::max(1, std::min(8, 4096 / std::max(M, 1)));
     ty = std::min(ty, std::max(1, nblocks));
-    g.block = dim3(32, ty, 1);
-    g.warp = true;
     g.tws = (long long)nblocks * C >= 64;    // real-time calls: a few transforms, table read through L1 instead
-  } else {                               // whole CTA per transform
-    g.block = dim3(std::min(512, M / 8), 1, 1);
-    g.warp = false; g.tws = (M <= 4096);
+  } else {
+    g.tws = (M <= 4096);
   }
-  g.grid = dim3((nblocks + g.block.y - 1) / g.block.y, C, 1);
+  g.block = dim3(nt, ty, 1);
+  g.grid = dim3((nblocks + ty - 1) / ty, C, 1);
   const size_t tl = g.tws ? (((size_t)pc::tw_table_len(M) + 15) & ~(size_t)15) : 0;
-  g.smem = (tl + (size_t)g.block.y * 2 * std::max(M, 16)) * sizeof(float2);
+  g.smem = (tl + (size_t)ty * 2 * std::max(M, 16)) * sizeof(float2);
   return g;
 }
+
+#if !defined(PC_EMULATE)
+template <int L>
+void launch_fwd_l(const pc::FwdParams& P, const FftGeom& g, cudaStream_t st) {
+  if (g.tws) pc::k_fwd_fft<(1 << L), true><<<g.grid, g.block, g.smem, st>>>(P);
+  else pc::k_fwd_fft<(1 << L), false><<<g.grid, g.block, g.smem, st>>>(P);
+}
+template <int L>
+void launch_inv_l(const pc::InvParams& P, const FftGeom& g, cudaStream_t st) {
+  if (g.tws) pc::k_inv_fft_ola<(1 << L), true><<<g.grid, g.block, g.smem, st>>>(P);
+  else pc::k_inv_fft_ola<(1 << L), false><<<g.grid, g.block, g.smem, st>>>(P);
+}
+template <int L>
+bool fft_set_smem_attr() {
+  const int kSmem = 200 * 1024;   // B = 4096: 48 KB table + 64 KB ping-pong buffers; B = 8192: 128 KB buffers
+  bool ok = cudaFuncSetAttribute(pc::k_fwd_fft<(1 << L), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<(1 << L), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  return ok;
+}
+#define PC_FOR_EACH_LOG2(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+#endif
 
 int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
   const FftGeom g = fft_geometry(P.M, P.nblocks, C);
@@ -198,10 +221,12 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
 #if defined(PC_EMULATE)
   pc::emu_fwd_fft({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  if (g.warp && g.tws) pc::k_fwd_fft<true, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
-  else if (g.warp) pc::k_fwd_fft<true, false><<<g.grid, g.block, g.smem, h->s_main>>>(P);
-  else if (g.tws) pc::k_fwd_fft<false, true><<<g.grid, g.block, g.smem, h->s_main>>>(P);
-  else pc::k_fwd_fft<false, false><<<g.grid, g.block, g.smem, h->s_main>>>(P);
+  switch (pc::ilog2(P.M)) {
+#define PC_CASE(L) case L: launch_fwd_l<L>(P, g, h->s_main); break;
+    PC_FOR_EACH_LOG2(PC_CASE)
+#undef PC_CASE
+    default: return fail(h, B200CONV_EINVAL, "unsupported transform size");
+  }
 #endif
   timing_end(h, id);
   h->launches++;
@@ -215,10 +240,12 @@ int launch_inv(b200conv* h, const pc::InvParams& P, int C, cudaStream_t st) {
 #if defined(PC_EMULATE)
   pc::emu_inv_fft_ola({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
-  if (g.warp && g.tws) pc::k_inv_fft_ola<true, true><<<g.grid, g.block, g.smem, st>>>(P);
-  else if (g.warp) pc::k_inv_fft_ola<true, false><<<g.grid, g.block, g.smem, st>>>(P);
-  else if (g.tws) pc::k_inv_fft_ola<false, true><<<g.grid, g.block, g.smem, st>>>(P);
-  else pc::k_inv_fft_ola<false, false><<<g.grid, g.block, g.smem, st>>>(P);
+  switch (pc::ilog2(P.M)) {
+#define PC_CASE(L) case L: launch_inv_l<L>(P, g, st); break;
+    PC_FOR_EACH_LOG2(PC_CASE)
+#undef PC_CASE
+    default: return fail(h, B200CONV_EINVAL, "unsupported transform size");
+  }
 #endif
   timing_end(h, id, st);
   h->launches++;
@@ -739,16 +766,15 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
   }
 #if !defined(PC_EMULATE)
   if (ok) {
-    // the FFT kernels need up to 192 KB of dynamic shared memory (B = 4096: table + ping-pong buffers)
-    const int kSmem = 200 * 1024;
-    ok = cudaFuncSetAttribute(pc::k_fwd_fft<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+    // function attributes are per device: set them once per device ordinal
+    static std::once_flag once[64];
+    static bool attr_ok = true;
+    std::call_once(once[h->cfg.device & 63], [] {
+#define PC_CASE(L) attr_ok = attr_ok && fft_set_smem_attr<L>();
+      PC_FOR_EACH_LOG2(PC_CASE)
+#undef PC_CASE
+    });
+    ok = attr_ok;
   }
 #endif
   if (!ok) {

@@ -44,16 +44,18 @@ PC_HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y
 PC_HD float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 PC_HD float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
 
-PC_HD int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+constexpr PC_HD int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // radix of the Stockham pass that starts with sub-transform length p (M total):
 // radix-8 wherever possible, the remainder as 4*4 / 4 / 2  (M = 512 -> 8,8,8; 128 -> 8,4,4; 8192 -> 8,8,8,4,4)
-PC_HD int pass_radix(int M, int p) {
+constexpr PC_HD int pass_radix(int M, int p) {
   const int l = ilog2(M / p);
-  if (l == 1) return 2;
-  if (l == 2 || l == 4) return 4;
-  return 8;
+  return l == 1 ? 2 : ((l == 2 || l == 4) ? 4 : 8);
 }
+
+// threads per transform of the FFT kernels: one warp up to M = 1024, the whole CTA above
+constexpr PC_HD int fft_threads(int M) { return M <= 1024 ? 32 : (M / 8 < 512 ? M / 8 : 512); }
+constexpr PC_HD bool fft_warp_mode(int M) { return M <= 1024; }
 
 // 4-point DFT in place (forward: e^{-2*pi*i/4}; INV: conjugate)
 template <bool INV>
@@ -82,23 +84,30 @@ PC_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
 // lanes consecutive words (the sum of (R-1)*p over the earlier passes telescopes to p-1).
 // ------------------------------------------------------------------------------------------
 PC_HD int swz(int a) { return a ^ ((a >> 4) & 7) ^ (((a >> 6) & 1) << 3); }
-PC_HD int tw_pass_offset(int M, int p) { return M / 2 + 1 + (p - 1); }
-PC_HD int tw_table_len(int M) { return M / 2 + 1 + (M - 1); }
+constexpr PC_HD int tw_pass_offset(int M, int p) { return M / 2 + 1 + (p - 1); }
+constexpr PC_HD int tw_table_len(int M) { return M / 2 + 1 + (M - 1); }
 
+// Accessors used by the butterflies.  swz() is linear over GF(2) (XOR of shifted copies of the
+// index), and inside a butterfly the base index (i resp. j) and the per-leg offsets (r*stride resp.
+// m*p) occupy disjoint bit ranges, hence swz(base + off) = swz(base) ^ swz(off): the base is
+// swizzled once per butterfly and every leg costs one XOR with a compile-time constant.
 struct SmemIn {
   const float2* buf;
-  PC_HD float2 operator()(int idx) const { return buf[swz(idx)]; }
+  PC_HD int prep(int base) const { return swz(base); }
+  PC_HD float2 at(int tok, int off) const { return buf[tok ^ swz(off)]; }
 };
 struct SmemOut {
   float2* buf;
-  PC_HD void operator()(int idx, float2 v) const { buf[swz(idx)] = v; }
+  PC_HD int prep(int base) const { return swz(base); }
+  PC_HD void put(int tok, int off, float2 v) const { buf[tok ^ swz(off)] = v; }
 };
 // forward first pass reads the time-domain block straight from global memory:
 // z[n] = x[2n] + i*x[2n+1], zero beyond the nv valid samples (the [x ; 0] padding is never stored)
 struct FwdGlobalIn {
   const float* src; int nv;
-  PC_HD float2 operator()(int n) const {
-    const int i0 = 2 * n, i1 = 2 * n + 1;
+  PC_HD int prep(int base) const { return base; }
+  PC_HD float2 at(int tok, int off) const {
+    const int i0 = 2 * (tok + off), i1 = i0 + 1;
     return make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
   }
 };
@@ -113,10 +122,12 @@ PC_HD void stockham_butterfly(In in, Out out, const float2* twp, int M, int p, i
   const int k = i & (p - 1);
   const int j = (i - k) * R + k;
   const int stride = M / R;
+  const int ti = in.prep(i);
+  const int to = out.prep(j);
   if (R == 8) {
     float2 a[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = in(i + r * stride);
+    for (int r = 0; r < 8; ++r) a[r] = in.at(ti, r * stride);
     if (k != 0) {
 #pragma unroll
       for (int r = 1; r < 8; ++r) {
@@ -145,27 +156,27 @@ PC_HD void stockham_butterfly(In in, Out out, const float2* twp, int M, int p, i
     dft4<INV>(a[4], a[5], a[6], a[7]);     // odd outputs  X[1], X[3], X[5], X[7]
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      out(j + (2 * m) * p, a[m]);
-      out(j + (2 * m + 1) * p, a[4 + m]);
+      out.put(to, (2 * m) * p, a[m]);
+      out.put(to, (2 * m + 1) * p, a[4 + m]);
     }
   } else if (R == 4) {
-    float2 a0 = in(i), a1 = in(i + stride), a2 = in(i + 2 * stride), a3 = in(i + 3 * stride);
+    float2 a0 = in.at(ti, 0), a1 = in.at(ti, stride), a2 = in.at(ti, 2 * stride), a3 = in.at(ti, 3 * stride);
     if (k != 0) {
       float2 w1 = twp[k], w2 = twp[p + k], w3 = twp[2 * p + k];
       if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       a1 = c_mul(a1, w1); a2 = c_mul(a2, w2); a3 = c_mul(a3, w3);
     }
     dft4<INV>(a0, a1, a2, a3);
-    out(j, a0); out(j + p, a1); out(j + 2 * p, a2); out(j + 3 * p, a3);
+    out.put(to, 0, a0); out.put(to, p, a1); out.put(to, 2 * p, a2); out.put(to, 3 * p, a3);
   } else {
-    float2 a0 = in(i), a1 = in(i + stride);
+    float2 a0 = in.at(ti, 0), a1 = in.at(ti, stride);
     if (k != 0) {
       float2 w1 = twp[k];
       if (INV) w1.y = -w1.y;
       a1 = c_mul(a1, w1);
     }
-    out(j, c_add(a0, a1));
-    out(j + p, c_sub(a0, a1));
+    out.put(to, 0, c_add(a0, a1));
+    out.put(to, p, c_sub(a0, a1));
   }
 }
 
@@ -175,7 +186,7 @@ PC_HD void stockham_butterfly(In in, Out out, const float2* twp, int M, int p, i
 // ------------------------------------------------------------------------------------------
 // load (only used when M == 1, i.e. no pass exists): z -> work buffer
 PC_HD void fwd_load(const float* src, int nv, float2* z, int M, int n) {
-  z[swz(n)] = FwdGlobalIn{src, nv}(n);
+  z[swz(n)] = FwdGlobalIn{src, nv}.at(n, 0);
 }
 
 // split: Z = FFT_M(z) (swizzled work buffer) -> packed spectrum row X (B = M entries), k in [0, M/2]
@@ -258,7 +269,9 @@ PC_HD void inv_store(const float2* z, int M, float scale, const OutSpec& o, int 
 // B = M output samples (n < M/2) of the 2M-point inverse transform are needed
 struct InvGlobalOut {
   const OutSpec* o; float scale; int half;
-  PC_HD void operator()(int n, float2 v) const {
+  PC_HD int prep(int base) const { return base; }
+  PC_HD void put(int tok, int off, float2 v) const {
+    const int n = tok + off;
     if (n >= half) return;
     inv_store_sample(v.x, scale, *o, 2 * n);
     inv_store_sample(v.y, scale, *o, 2 * n + 1);
@@ -405,7 +418,11 @@ struct float4c { float2 a, b; };   // two adjacent bins
 
 PC_HD float4c ld_pair(const float2* p) {
 #if defined(__CUDA_ARCH__)
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  // volatile asm keeps the loads of one batch back to back (issued before any dependent math):
+  // the streaming sweep lives on memory-level parallelism
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   float4c r; r.a = make_float2(v.x, v.y); r.b = make_float2(v.z, v.w); return r;
 #else
   float4c r; r.a = p[0]; r.b = p[1]; return r;
@@ -556,36 +573,84 @@ struct StreamParams {
 // ==========================================================================================
 
 
-// FFT kernel geometry: block (tx, ty) = tx threads per transform, ty transforms per CTA.
-//   WARP = true : tx == 32, one warp owns one transform -> passes are separated by __syncwarp()
-//                 only (no CTA-wide barrier after the twiddle preload), warps run decoupled.
-//   TWS  = true : the twiddle table (2M float2) is staged in shared memory once per CTA.
-// dynamic smem = (TWS ? 2M : 0) + ty * 2M float2.  grid (ceil(nblocks/ty), C).
+// FFT kernels, templated on the transform size M (= B) so that every index, radix, stride and
+// trip count is a compile-time constant (the passes unroll completely; no integer division).
+//   block (NT, ty): NT = fft_threads(M) threads per transform, ty transforms per CTA, grid (ceil(nblocks/ty), C)
+//   M <= 1024 : NT = 32, one WARP owns one transform -> passes separated by __syncwarp() only
+//   M >  1024 : NT = min(512, M/8), the CTA owns one transform (ty = 1), __syncthreads()
+//   TWS       : the twiddle table (3M/2 float2) is staged in shared memory once per CTA
+// dynamic smem = (TWS ? roundup16(3M/2) : 0) + ty * 2 * max(M,16) float2.
+
 template <bool WARP>
 __device__ __forceinline__ void fft_sync() {
   if (WARP) __syncwarp(); else __syncthreads();
 }
 
-template <bool WARP, bool TWS>
-__global__ void k_fwd_fft(FwdParams P) {
+// passes P, P*R, ... of an M-point transform between two work buffers; returns the buffer holding the result
+template <bool INV, int M, int P>
+__device__ __forceinline__ float2* fft_mid_passes(float2* in, float2* out, const float2* tw, int tx, bool active) {
+  if constexpr (P >= M) {
+    return in;
+  } else {
+    constexpr int R = pass_radix(M, P);
+    constexpr int NT = fft_threads(M);
+    if constexpr (INV && P * R == M) {
+      return in;                                    // the inverse kernel runs its last pass itself
+    } else {
+      if (active) {
+#pragma unroll
+        for (int i0 = 0; i0 < M / R; i0 += NT) {
+          const int i = i0 + tx;
+          if (M / R >= NT || i < M / R)
+            stockham_butterfly<INV>(SmemIn{in}, SmemOut{out}, tw + tw_pass_offset(M, P), M, P, R, i);
+        }
+      }
+      fft_sync<fft_warp_mode(M)>();
+      return fft_mid_passes<INV, M, P * R>(out, in, tw, tx, active);
+    }
+  }
+}
+
+
+// runs the LAST pass of the M-point inverse transform (the pass whose output length reaches M)
+template <int M, int P>
+__device__ __forceinline__ void last_inverse_pass(const float2* in, const float2* tw, int tx, const OutSpec& o, float scale) {
+  constexpr int R = pass_radix(M, P);
+  if constexpr (P * R == M) {
+    constexpr int NT = fft_threads(M);
+#pragma unroll
+    for (int i0 = 0; i0 < M / R; i0 += NT) {
+      const int i = i0 + tx;
+      if (M / R >= NT || i < M / R)
+        stockham_butterfly<true>(SmemIn{in}, InvGlobalOut{&o, scale, M / 2}, tw + tw_pass_offset(M, P), M, P, R, i);
+    }
+  } else {
+    last_inverse_pass<M, P * R>(in, tw, tx, o, scale);
+  }
+}
+
+template <int M, bool TWS>
+__global__ void __launch_bounds__(512) k_fwd_fft(FwdParams P) {
   extern __shared__ float2 pc_smem[];
-  const int M = P.M;
-  const int tx = threadIdx.x, nth = blockDim.x;
+  constexpr bool WARP = fft_warp_mode(M);
+  constexpr int NT = fft_threads(M);
+  const int tx = threadIdx.x;
   const int blk = blockIdx.x * blockDim.y + threadIdx.y;
   const int c = blockIdx.y;
   const bool active = blk < P.nblocks;
   const float2* tw = P.tw;
   float2* data = pc_smem;
   if (TWS) {
-    const int tl = tw_table_len(M);
+    constexpr int tl = tw_table_len(M);
     const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
     for (int j = tid; j < tl; j += nthr) pc_smem[j] = P.tw[j];
     tw = pc_smem;
     data = pc_smem + ((tl + 15) & ~15);
     __syncthreads();
   }
-  float2* bufA = data + (size_t)threadIdx.y * 2 * M;
-  float2* bufB = bufA + M;
+  constexpr int MB = M < 16 ? 16 : M;
+  float2* bufA = data + (size_t)threadIdx.y * 2 * MB;
+  float2* bufB = bufA + MB;
   int nv = 0;
   const float* src = nullptr;
   if (active) {
@@ -594,29 +659,27 @@ __global__ void k_fwd_fft(FwdParams P) {
     nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
     src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
   }
-  float2* in = bufA; float2* out = bufB;
-  if (M == 1) {
-    if (active && tx == 0) fwd_load(src, nv, in, M, 0);
+  float2* res = bufA;
+  if constexpr (M == 1) {
+    if (active && tx == 0) fwd_load(src, nv, bufA, M, 0);
   } else {
     // first pass straight from global memory (zero padding applied in the accessor)
-    const int R0 = pass_radix(M, 1);
-    if (active)
-      for (int i = tx; i < M / R0; i += nth)
-        stockham_butterfly<false>(FwdGlobalIn{src, nv}, SmemOut{in}, tw + tw_pass_offset(M, 1), M, 1, R0, i);
-    fft_sync<WARP>();
-    for (int p = R0; p < M;) {
-      const int R = pass_radix(M, p);
-      if (active)
-        for (int i = tx; i < M / R; i += nth)
-          stockham_butterfly<false>(SmemIn{in}, SmemOut{out}, tw + tw_pass_offset(M, p), M, p, R, i);
-      fft_sync<WARP>();
-      float2* t = in; in = out; out = t;
-      p *= R;
+    constexpr int R0 = pass_radix(M, 1);
+    if (active) {
+#pragma unroll
+      for (int i0 = 0; i0 < M / R0; i0 += NT) {
+        const int i = i0 + tx;
+        if (M / R0 >= NT || i < M / R0)
+          stockham_butterfly<false>(FwdGlobalIn{src, nv}, SmemOut{bufA}, tw + tw_pass_offset(M, 1), M, 1, R0, i);
+      }
     }
+    fft_sync<WARP>();
+    res = fft_mid_passes<false, M, R0>(bufA, bufB, tw, tx, active);
   }
   if (active) {
     float2* X = P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)M;
-    for (int k = tx; k <= M / 2; k += nth) fwd_split(in, X, tw, M, k);
+#pragma unroll 4
+    for (int k = tx; k <= M / 2; k += NT) fwd_split(res, X, tw, M, k);
   }
 }
 
@@ -641,26 +704,28 @@ __global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
 
 
 // same geometry as k_fwd_fft
-template <bool WARP, bool TWS>
-__global__ void k_inv_fft_ola(InvParams P) {
+template <int M, bool TWS>
+__global__ void __launch_bounds__(512) k_inv_fft_ola(InvParams P) {
   extern __shared__ float2 pc_smem[];
-  const int M = P.M;
-  const int tx = threadIdx.x, nth = blockDim.x;
+  constexpr bool WARP = fft_warp_mode(M);
+  constexpr int NT = fft_threads(M);
+  const int tx = threadIdx.x;
   const int blk = blockIdx.x * blockDim.y + threadIdx.y;
   const int c = blockIdx.y;
   const bool active = blk < P.nblocks;
   const float2* tw = P.tw;
   float2* data = pc_smem;
   if (TWS) {
-    const int tl = tw_table_len(M);
+    constexpr int tl = tw_table_len(M);
     const int tid = threadIdx.y * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
     for (int j = tid; j < tl; j += nthr) pc_smem[j] = P.tw[j];
     tw = pc_smem;
     data = pc_smem + ((tl + 15) & ~15);
     __syncthreads();                    // inv_pre already needs the table
   }
-  float2* bufA = data + (size_t)threadIdx.y * 2 * M;
-  float2* bufB = bufA + M;
+  constexpr int MB = M < 16 ? 16 : M;
+  float2* bufA = data + (size_t)threadIdx.y * 2 * MB;
+  float2* bufB = bufA + MB;
   OutSpec o;
   if (active) {
     o.dst = P.dst + (long long)c * P.dst_cstride;
@@ -675,29 +740,16 @@ __global__ void k_inv_fft_ola(InvParams P) {
     o.abs0 = P.abs0 + (long long)blk * M;
     const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
     const float2* Yp = Yt - P.y_rstride;
-    for (int k = tx; k <= M / 2; k += nth) inv_pre(Yt, Yp, bufA, tw, M, k);
+#pragma unroll 4
+    for (int k = tx; k <= M / 2; k += NT) inv_pre(Yt, Yp, bufA, tw, M, k);
   }
   fft_sync<WARP>();
-  float2* in = bufA; float2* out = bufB;
-  if (M == 1) {
-    if (active && tx == 0) inv_store(in, M, P.scale, o, 0);
+  if constexpr (M == 1) {
+    if (active && tx == 0) inv_store(bufA, M, P.scale, o, 0);
   } else {
-    for (int p = 1; p < M;) {
-      const int R = pass_radix(M, p);
-      const bool last = p * R == M;
-      if (active) {
-        if (!last) {
-          for (int i = tx; i < M / R; i += nth)
-            stockham_butterfly<true>(SmemIn{in}, SmemOut{out}, tw + tw_pass_offset(M, p), M, p, R, i);
-        } else {      // last pass: scaled samples straight to the destination (first half only)
-          for (int i = tx; i < M / R; i += nth)
-            stockham_butterfly<true>(SmemIn{in}, InvGlobalOut{&o, P.scale, M / 2}, tw + tw_pass_offset(M, p), M, p, R, i);
-        }
-      }
-      if (!last) fft_sync<WARP>();
-      float2* t = in; in = out; out = t;
-      p *= R;
-    }
+    float2* in = fft_mid_passes<true, M, 1>(bufA, bufB, tw, tx, active);   // all passes but the last
+    // last pass: scaled samples straight to the destination (first half of the transform only)
+    if (active) last_inverse_pass<M, 1>(in, tw, tx, o, P.scale);
   }
 }
 

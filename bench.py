@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -109,7 +109,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed steps + 0.6 s continuation of the same step loop"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -288,6 +289,14 @@ def main():
         barrier()
         t_w1 = time.perf_counter()
         launches = eng.launch_count - launches0
+        if sampler:
+            # K short steps give nvidia-smi (>= 20 ms per sample) almost nothing to see: keep the very same
+            # step loop running for another ~0.6 s (untimed) so that the clock/throttle record is meaningful
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                step_device()
+                torch.cuda.synchronize()
+            t_w1 = time.perf_counter()
         t_tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_tot, op=dist.ReduceOp.MAX)
@@ -364,11 +373,11 @@ def main():
         return res
 
     WL0 = wl
-    T = args.blocks or (7104 if args.workload != "ir120" else 2368)
+    T = args.blocks or 7104
     main_res = run_workload(wl, T, args.steps, with_e2e=not args.no_e2e, with_clocks=True)
     extra = None
     if args.also_ir120 and args.workload == "metric":
-        r = run_workload(dict(WORKLOADS["ir120"]), 2368, max(2, min(3, args.steps)), with_e2e=False, with_clocks=False)
+        r = run_workload(dict(WORKLOADS["ir120"]), 7104, max(2, min(3, args.steps)), with_e2e=False, with_clocks=False)
         extra = {"value": r["value"], "unit": "M stereo frames/s", "ms_per_step": r["ms_per_step"], "config": r["config"],
                  "roofline_frac": r["roofline"]["frac"], "fp32_frac": r["roofline"]["fp32"]["frac"]}
 

@@ -230,7 +230,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -289,19 +290,20 @@ def main():
         barrier()
         t_w1 = time.perf_counter()
         launches = eng.launch_count - launches0
-        if sampler:
-            # K short steps give nvidia-smi (>= 20 ms per sample) almost nothing to see: keep the very same
-            # step loop running for another ~0.6 s (untimed) so that the clock/throttle record is meaningful
-            t_end = time.perf_counter() + 0.6
-            while time.perf_counter() < t_end:
-                step_device()
-                torch.cuda.synchronize()
-            t_w1 = time.perf_counter()
         t_tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_tot, op=dist.ReduceOp.MAX)
         ms_per_step = float(t_tot.item()) / steps
         value = n / (ms_per_step * 1e-3) / 1e6
+        if with_clocks:
+            # K short steps give nvidia-smi (>= 20 ms per sample) almost nothing to see: EVERY rank keeps the very
+            # same step loop running for another ~0.6 s (untimed; identical count on all ranks — the reduce is a
+            # collective) so that the clock / throttle record of rank 0 is meaningful
+            n_extra = int(min(2000, max(1, 600.0 / max(ms_per_step, 0.05))))
+            for _ in range(n_extra):
+                step_device()
+            barrier()
+            t_w1 = time.perf_counter()
         clocks = sampler.stop(t_w0, t_w1) if sampler else None
 
         # dominant-kernel roofline: CUDA events around every FDL-sweep launch (separate pass)

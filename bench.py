@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="print a per-variant timing table to stderr")
+    ap.add_argument("--mgpu", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange path (N > 1)")
     ap.add_argument("--also-ir120", dest="also_ir120", action="store_true",
                     help="additionally time config 5 (120 s IR) and attach it as `ir120`")
     args = ap.parse_args()
@@ -222,7 +223,7 @@ def main():
     import torch
     import torch.distributed as dist
     from reevr_b200.convolver import Engine
-    from reevr_b200.distributed import attach_reduce
+    from reevr_b200.distributed import attach_p2p, attach_reduce
     from reevr_b200.synth import synth_input, synth_ir
 
     if not torch.cuda.is_available():
@@ -257,8 +258,18 @@ def main():
         P = int(st["partitions"])
         Ploc = int(st["p_end"]) - int(st["p_begin"])
         stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+        mgpu_path = "single GPU"
         if world > 1:
-            attach_reduce(eng, device=local)
+            attach_reduce(eng, device=local)          # NCCL reduce hook (always installed)
+            mgpu_path = "partition-range shards + NCCL reduce of partial spectra to rank 0"
+            if args.mgpu == "p2p":
+                try:
+                    attach_p2p(eng)                   # fused slot exchange over NVLink peer memory
+                    mgpu_path = ("partition-range shards + fused slot exchange: sweep epilogue stores partial rows into "
+                                 "the owner GPU's slot over NVLink, flag barrier, per-slice inverse FFT (no NCCL on the data path)")
+                except Exception as ex:               # both are GPU paths; say which one ran
+                    print(f"[bench] p2p attach failed on rank {rank}: {ex}; using the NCCL reduce path", file=sys.stderr)
+                    mgpu_path += f" (p2p attach failed: {ex})"
 
         x_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
         for c in range(C):
@@ -355,8 +366,7 @@ def main():
             "value": value, "ms_per_step": ms_per_step, "launches": int(launches), "clocks": clocks, "e2e": e2e,
             "config": {"workload": wl["desc"], "channels": C, "ir_taps": eng.ir_len(0), "block": block, "partitions": P,
                        "blocks_per_step": T, "frames_per_step": n, "launch_groups_per_step": groups,
-                       "parallelism": "single GPU" if world == 1 else
-                       f"partition-range shards x{world} ({Ploc} partitions on rank 0) + NCCL reduce of partial spectra to rank 0",
+                       "parallelism": mgpu_path if world == 1 else f"x{world}: {mgpu_path} ({Ploc} partitions on rank 0)",
                        "l2": "flushed between timed steps (256 MB write)", "init_s": round(t_init, 4)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,

@@ -109,6 +109,21 @@ void*  b200conv_stream(const b200conv_t* h);                  /* cudaStream_t of
 typedef int (*b200conv_reduce_fn)(void* user, float* dev_buf, size_t n_floats, void* cuda_stream);
 int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
 
+/* Fused multi-GPU path ("slot exchange", uniform single-stage handles with shard_count > 1):
+ * the sweep kernel's epilogue stores each partial spectrum row straight into the exchange buffer of
+ * the GPU that owns the row's time slice (peer memory over NVLink), a flag barrier follows, every
+ * GPU runs the inverse FFT on its own slice (summing the shard_count partial slots while loading)
+ * and writes the audio directly into shard 0's output exchange buffer.  No NCCL call on the data
+ * path.  Set-up: every shard exports a blob, the caller all-gathers the blobs (rank order) and
+ * every shard imports the concatenation.  mode 0 = CUDA IPC handles (one process per GPU),
+ * mode 1 = raw pointers (all shards in one process on one device; tests). */
+size_t b200conv_p2p_blob_size(const b200conv_t* h);
+int    b200conv_p2p_export(b200conv_t* h, void* blob, int mode);
+int    b200conv_p2p_import(b200conv_t* h, const void* all_blobs /* shard_count * blob_size bytes */);
+/* Host-side barrier used instead of the flag kernel by the CPU emulation build (tests only). */
+typedef int (*b200conv_barrier_fn)(void* user);
+int    b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* user);
+
 /* Pinned host memory helpers (staging buffers for the e2e path). */
 void* b200conv_alloc_host(size_t bytes);
 void  b200conv_free_host(void* p);

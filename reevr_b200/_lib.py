@@ -36,6 +36,7 @@ class StageInfo(C.Structure):
 
 
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 # every symbol include/b200conv.h declares: (name, restype, argtypes)
 _PP = C.POINTER(C.c_void_p)
@@ -58,6 +59,10 @@ SYMBOLS = [
     ("b200conv_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("b200conv_stream", C.c_void_p, [C.c_void_p]),
     ("b200conv_set_reduce", C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
+    ("b200conv_p2p_blob_size", C.c_size_t, [C.c_void_p]),
+    ("b200conv_p2p_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("b200conv_p2p_import", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("b200conv_p2p_set_host_barrier", C.c_int, [C.c_void_p, BARRIER_FN, C.c_void_p]),
     ("b200conv_alloc_host", C.c_void_p, [C.c_size_t]),
     ("b200conv_free_host", None, [C.c_void_p]),
     ("b200conv_version", C.c_char_p, []),

@@ -138,6 +138,28 @@ class Engine:
         self._reduce_cb = _lib.REDUCE_FN(tramp)
         self._l.b200conv_set_reduce(self._h, self._reduce_cb, None)
 
+    def p2p_attach(self, allgather, mode: int = 0, host_barrier=None):
+        """Enables the fused multi-GPU path (slot exchange over peer memory, see b200conv.h).
+        `allgather(blob: bytes) -> list[bytes]` must return every shard's blob in rank order.
+        mode 0 = CUDA IPC (one process per GPU), 1 = raw pointers (all shards in this process).
+        `host_barrier` (callable -> 0) replaces the flag kernel in the CPU emulation build."""
+        if host_barrier is not None:
+            def tramp(_user):
+                try:
+                    return int(host_barrier() or 0)
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._barrier_cb = _lib.BARRIER_FN(tramp)
+            self._l.b200conv_p2p_set_host_barrier(self._h, self._barrier_cb, None)
+        n = self._l.b200conv_p2p_blob_size(self._h)
+        blob = C.create_string_buffer(n)
+        self._check(self._l.b200conv_p2p_export(self._h, blob, mode), "p2p_export")
+        blobs = allgather(blob.raw)
+        joined = C.create_string_buffer(b"".join(blobs), n * len(blobs))
+        self._check(self._l.b200conv_p2p_import(self._h, joined), "p2p_import")
+
     def close(self):
         if getattr(self, "_h", None):
             self._l.b200conv_destroy(self._h)

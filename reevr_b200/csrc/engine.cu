@@ -102,6 +102,24 @@ struct b200conv {
   b200conv_reduce_fn reduce = nullptr;
   void* reduce_user = nullptr;
   int n_sm = 148;
+  // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
+  bool p2p_on = false;
+  int p2p_mode = 0;
+  int xSR = 0;                       // rows per slot (slice rows + halo + spare)
+  size_t xslot = 0;                  // float2 per slot
+  float2* Yx[2] = {nullptr, nullptr};       // [G slots][xSR][C][B]
+  float2* Hh = nullptr;                     // [3][G][C][B] halo of the next group's first slice (owner 0)
+  float* xout[2] = {nullptr, nullptr};      // [C][Lmax] output exchange (used on shard 0)
+  unsigned int* xflags = nullptr;           // 8 barrier words + 1 error word
+  int hidx = 0;                             // halo buffer in use (mod 3)
+  unsigned int bar_epoch = 0;
+  float2* peerYx[8][2] = {};
+  float2* peerHh0 = nullptr;
+  float* peer_xout0[2] = {nullptr, nullptr};
+  unsigned int* peer_flags[8] = {};
+  std::vector<void*> ipc_opened;
+  b200conv_barrier_fn host_barrier = nullptr;
+  void* host_barrier_user = nullptr;
 };
 
 namespace {
@@ -127,7 +145,18 @@ void free_stage(Stage& s) {
   s = Stage();
 }
 
+void p2p_release(b200conv* h) {
+#if !defined(PC_EMULATE)
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+#endif
+  h->ipc_opened.clear();
+  cudaFree(h->Yx[0]); cudaFree(h->Yx[1]); cudaFree(h->Hh); cudaFree(h->xout[0]); cudaFree(h->xout[1]); cudaFree(h->xflags);
+  h->Yx[0] = h->Yx[1] = nullptr; h->Hh = nullptr; h->xout[0] = h->xout[1] = nullptr; h->xflags = nullptr;
+  h->p2p_on = false; h->hidx = 0; h->bar_epoch = 0;
+}
+
 void free_all(b200conv* h) {
+  p2p_release(h);
   for (auto& s : h->stages) free_stage(s);
   h->stages.clear();
   for (int i = 0; i < 2; ++i) {
@@ -370,6 +399,7 @@ int launch_cmac_stream_rows(b200conv* h, const pc::CmacParams& P, int C) {
 // P.Ppad enters as the number of real (unpadded) partition rows of this shard
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
+  if (P.xg > 0) variant = (P.nblocks >= 64) ? 22 : 26;     // slot exchange: only the packed-FMA sweeps carry the exchange epilogue
   if (variant == 0) {
     // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
     // launch group is long enough to fill 16-block tiles, TT = 8 below that)
@@ -536,6 +566,13 @@ int clear_state(b200conv* h) {
     s.fill = 0;
   }
   h->abs_pos = 0;
+  if (h->Yx[0]) {
+    const Stage& s0 = h->stages[0];
+    const size_t row = (size_t)h->C * s0.B;
+    for (int i = 0; i < 2; ++i) CU_CHECK(h, cudaMemsetAsync(h->Yx[i], 0, (size_t)h->cfg.shard_count * h->xslot * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(h->Hh, 0, (size_t)3 * h->cfg.shard_count * row * sizeof(float2), h->s_main));
+    h->hidx = 0;
+  }
   return 0;
 }
 
@@ -601,12 +638,156 @@ int compact_timeline(b200conv* h, Stage& s) {
   return 0;
 }
 
+
+// ---- slot exchange (fused multi-GPU path) ------------------------------------------------------
+struct P2PRecord { unsigned long long kind; unsigned long long ptr; unsigned char ipc[64]; };
+constexpr int kP2PBuffers = 6;    // Yx[0], Yx[1], Hh, xout[0], xout[1], flags
+
+int p2p_alloc(b200conv* h) {
+  if (h->Yx[0]) return 0;
+  const Stage& s = h->stages[0];
+  const int G = h->cfg.shard_count, C = h->C, B = s.B;
+  const size_t row = (size_t)C * B;
+  h->xSR = (s.Tcap + G - 1) / G + 2;
+  h->xslot = (size_t)h->xSR * row;
+  for (int i = 0; i < 2; ++i) {
+    CU_CHECK(h, cudaMalloc(&h->Yx[i], (size_t)G * h->xslot * sizeof(float2)));
+    CU_CHECK(h, cudaMemsetAsync(h->Yx[i], 0, (size_t)G * h->xslot * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMalloc(&h->xout[i], (size_t)C * h->Lmax * sizeof(float)));
+  }
+  CU_CHECK(h, cudaMalloc(&h->Hh, (size_t)3 * G * row * sizeof(float2)));
+  CU_CHECK(h, cudaMemsetAsync(h->Hh, 0, (size_t)3 * G * row * sizeof(float2), h->s_main));
+  CU_CHECK(h, cudaMalloc(&h->xflags, 16 * sizeof(unsigned int)));
+  CU_CHECK(h, cudaMemsetAsync(h->xflags, 0, 16 * sizeof(unsigned int), h->s_main));
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  return 0;
+}
+
+// after a host synchronisation: did a flag barrier give up waiting for a peer?
+int p2p_check(b200conv* h) {
+#if !defined(PC_EMULATE)
+  if (h->p2p_on) {
+    unsigned int err = 0;
+    CU_CHECK(h, cudaMemcpy(&err, h->xflags + 8, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err != 0) return fail(h, B200CONV_ECUDA, "slot-exchange barrier timed out waiting for a peer GPU");
+  }
+#else
+  (void)h;
+#endif
+  return 0;
+}
+
+int p2p_barrier(b200conv* h, cudaStream_t st) {
+  h->bar_epoch++;
+#if defined(PC_EMULATE)
+  (void)st;
+  if (!h->host_barrier) return fail(h, B200CONV_ESTATE, "emulated slot exchange needs a host barrier");
+  if (h->host_barrier(h->host_barrier_user) != 0) return fail(h, B200CONV_ECUDA, "host barrier failed");
+#else
+  pc::BarrierParams bp{};
+  for (int g = 0; g < h->cfg.shard_count; ++g) bp.peer_flags[g] = h->peer_flags[g];
+  bp.my_flags = h->xflags;
+  bp.error_word = h->xflags + 8;
+  bp.rank = h->cfg.shard_rank; bp.G = h->cfg.shard_count; bp.epoch = h->bar_epoch;
+  pc::k_p2p_barrier<<<1, 32, 0, st>>>(bp);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+#endif
+  return 0;
+}
+
+// one launch group of a single-stage sharded handle through the slot exchange
+int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n) {
+  const int C = h->C, G = h->cfg.shard_count, g = h->cfg.shard_rank;
+  Stage& s = h->stages[0];
+  const int B = s.B;
+  const size_t row = (size_t)C * B;
+  cudaStream_t ps = h->s_post;
+  if (n == 0) return 0;
+  if (n + B > h->Lmax) return fail(h, B200CONV_ESTATE, "launch group larger than the staging buffers");
+  const size_t total = (size_t)s.fill + n;
+  const int complete = (int)(total / B);
+  const int partial = (int)(total % B);
+  const int nb = complete + (partial > 0 ? 1 : 0);
+  const bool direct = (s.fill == 0);
+  if (!direct)
+    CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                  n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+  const int yb = s.ybuf;
+  const int per = (nb + G - 1) / G;
+  if (s.head + nb + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
+  pc::FwdParams fp{};
+  fp.src = direct ? in_dev : s.inbuf;
+  fp.src_cstride = direct ? (long long)in_stride : (long long)s.in_stride;
+  fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
+  fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
+  fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+  if (int rc = launch_fwd(h, fp, C)) return rc;
+
+  // the exchange buffers of parity yb are free once every GPU finished the inverse FFT of two groups ago
+  CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb], 0));
+  pc::CmacParams cp{};
+  cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
+  cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
+  cp.Y = nullptr; cp.y_cstride = B; cp.y_rstride = (long long)row; cp.yrow0 = 0;
+  cp.B = B; cp.Ppad = s.P; cp.nblocks = nb;
+  cp.xg = G; cp.xrank = g; cp.xper = per; cp.xslot = (long long)h->xslot;
+  cp.xhalo_block = complete > 0 ? complete - 1 : -1;
+  for (int r = 0; r < G; ++r) cp.xbase[r] = h->peerYx[r][yb];
+  cp.xhalo = h->peerHh0 + (size_t)((h->hidx + 1) % 3) * G * row;
+  if (int rc = launch_cmac(h, cp, C)) return rc;
+  CU_CHECK(h, cudaEventRecord(s.ev_sweep[yb], h->s_main));
+  CU_CHECK(h, cudaStreamWaitEvent(ps, s.ev_sweep[yb], 0));
+
+  if (int rc = p2p_barrier(h, ps)) return rc;          // every GPU's partial rows have landed
+
+  const int j0 = std::min(nb, g * per), j1 = std::min(nb, (g + 1) * per);
+  if (j1 > j0) {
+    if (g == 0)   // halo of the first slice = last completed row of the previous group (all G partials)
+      CU_CHECK(h, cudaMemcpy2DAsync(h->Yx[yb], h->xslot * sizeof(float2), h->Hh + (size_t)h->hidx * G * row,
+                                    row * sizeof(float2), row * sizeof(float2), G, cudaMemcpyDeviceToDevice, ps));
+    pc::InvParams ip{};
+    ip.Y = h->Yx[yb]; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
+    ip.tw = s.tw; ip.M = B; ip.nblocks = j1 - j0; ip.scale = 1.0f / (float)B;
+    ip.n_partials = G; ip.partial_stride = (long long)h->xslot;
+    ip.dst = h->peer_xout0[yb]; ip.dst_cstride = (long long)h->Lmax;
+    ip.index0 = -(long long)s.fill + (long long)j0 * B; ip.lo = 0; ip.hi = (long long)n; ip.mask = -1;
+    ip.n_add = 0; ip.abs0 = 0;
+    if (int rc = launch_inv(h, ip, C, ps)) return rc;
+  }
+  if (int rc = p2p_barrier(h, ps)) return rc;          // every slice of the audio is in shard 0's exchange buffer
+  if (g == 0 && out_dev)
+    CU_CHECK(h, cudaMemcpy2DAsync(out_dev, out_stride * sizeof(float), h->xout[yb], h->Lmax * sizeof(float),
+                                  n * sizeof(float), C, cudaMemcpyDeviceToDevice, ps));
+  CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
+
+  if (complete > 0) {
+    s.ybuf = yb ^ 1;
+    h->hidx = (h->hidx + 1) % 3;
+    if (partial > 0) {
+      const float* tail_src = direct ? in_dev + (size_t)complete * B : s.inbuf + (size_t)complete * B;
+      const size_t tail_pitch = direct ? in_stride : s.in_stride;
+      CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), tail_src, tail_pitch * sizeof(float),
+                                    partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+    }
+    s.head += complete;
+    s.blocks_done += complete;
+  } else if (direct && partial > 0) {
+    CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                  partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+  }
+  s.fill = partial;
+  h->abs_pos += (long long)n;
+  return 0;
+}
+
 // `overlap`: reduce + inverse FFT go to s_post so that they overlap the next group's forward
 // FFT + sweep on s_main (double-buffered Y); otherwise everything is issued on s_main.
 int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n,
               bool overlap) {
   const int C = h->C;
   const bool root = h->cfg.shard_rank == 0;
+  if (h->p2p_on) return run_group_p2p(h, in_dev, in_stride, out_dev, out_stride, n);
   cudaStream_t ps = overlap ? h->s_post : h->s_main;
   if (n == 0) return 0;
   if (n + h->stages[0].B > h->Lmax) return fail(h, B200CONV_ESTATE, "launch group larger than the staging buffers");
@@ -857,7 +1038,7 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
   } else {
     const size_t B0 = h->stages[0].B;
     const size_t chunk = h->Lmax - B0;     // keeps fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
-    const bool overlap = len > chunk || h->cfg.shard_count > 1;
+    const bool overlap = len > chunk || h->cfg.shard_count > 1;    // (slot-exchange groups always use s_post)
     size_t done = 0;
     while (done < len) {
       size_t n = std::min(len - done, chunk);
@@ -869,6 +1050,7 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
   if (sync || h->timing) {
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
     if (h->timing) timing_collect(h);
+    if (int rc = p2p_check(h)) return rc;
   }
   return B200CONV_OK;
 }
@@ -983,6 +1165,87 @@ void* b200conv_stream(const b200conv_t* h) { return h ? (void*)h->s_main : nullp
 int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user) {
   if (!h) return B200CONV_EINVAL;
   h->reduce = fn; h->reduce_user = user;
+  return B200CONV_OK;
+}
+
+size_t b200conv_p2p_blob_size(const b200conv_t* h) { (void)h; return sizeof(P2PRecord) * kP2PBuffers; }
+
+int b200conv_p2p_export(b200conv_t* h, void* blob, int mode) {
+  REQUIRE_CUDA(h);
+  if (!blob) return fail(h, B200CONV_EINVAL, "null blob");
+  if (h->cfg.shard_count < 2 || h->cfg.shard_count > 8) return fail(h, B200CONV_ESTATE, "slot exchange needs 2..8 shards");
+  if (h->stages.size() != 1) return fail(h, B200CONV_ESTATE, "slot exchange supports uniform (single-stage) handles");
+  if (int rc = set_device(h)) return rc;
+  if (int rc = p2p_alloc(h)) return rc;
+  h->p2p_mode = mode;
+  void* bufs[kP2PBuffers] = {h->Yx[0], h->Yx[1], h->Hh, h->xout[0], h->xout[1], h->xflags};
+  P2PRecord* rec = static_cast<P2PRecord*>(blob);
+  for (int i = 0; i < kP2PBuffers; ++i) {
+    std::memset(&rec[i], 0, sizeof(P2PRecord));
+    rec[i].ptr = (unsigned long long)(uintptr_t)bufs[i];
+#if defined(PC_EMULATE)
+    rec[i].kind = 1;
+#else
+    if (mode == 1) {
+      rec[i].kind = 1;
+    } else {
+      rec[i].kind = 2;
+      cudaIpcMemHandle_t hd;
+      CU_CHECK(h, cudaIpcGetMemHandle(&hd, bufs[i]));
+      static_assert(sizeof(hd) == 64, "IPC handle size");
+      std::memcpy(rec[i].ipc, &hd, 64);
+    }
+#endif
+  }
+  return B200CONV_OK;
+}
+
+int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
+  REQUIRE_CUDA(h);
+  if (!all_blobs || !h->Yx[0]) return fail(h, B200CONV_ESTATE, "export before import");
+  if (int rc = set_device(h)) return rc;
+  const int G = h->cfg.shard_count, me = h->cfg.shard_rank;
+  const P2PRecord* rec = static_cast<const P2PRecord*>(all_blobs);
+  for (int r = 0; r < G; ++r) {
+    void* ptrs[kP2PBuffers];
+    for (int i = 0; i < kP2PBuffers; ++i) {
+      const P2PRecord& x = rec[r * kP2PBuffers + i];
+      if (r == me || x.kind == 1) {
+        ptrs[i] = (void*)(uintptr_t)x.ptr;
+      } else {
+#if defined(PC_EMULATE)
+        return fail(h, B200CONV_EINVAL, "IPC records in the emulation build");
+#else
+        // only the buffers this shard touches are mapped: every peer's Yx + flags, shard 0's Hh + xout
+        const bool needed = (i <= 1) || (i == 5) || (r == 0);
+        ptrs[i] = nullptr;
+        if (needed) {
+          cudaIpcMemHandle_t hd;
+          std::memcpy(&hd, x.ipc, 64);
+          void* p = nullptr;
+          CU_CHECK(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+          h->ipc_opened.push_back(p);
+          ptrs[i] = p;
+        }
+#endif
+      }
+    }
+    h->peerYx[r][0] = static_cast<float2*>(ptrs[0]);
+    h->peerYx[r][1] = static_cast<float2*>(ptrs[1]);
+    h->peer_flags[r] = static_cast<unsigned int*>(ptrs[5]);
+    if (r == 0) {
+      h->peerHh0 = static_cast<float2*>(ptrs[2]);
+      h->peer_xout0[0] = static_cast<float*>(ptrs[3]);
+      h->peer_xout0[1] = static_cast<float*>(ptrs[4]);
+    }
+  }
+  h->p2p_on = true;
+  return B200CONV_OK;
+}
+
+int b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* user) {
+  if (!h) return B200CONV_EINVAL;
+  h->host_barrier = fn; h->host_barrier_user = user;
   return B200CONV_OK;
 }
 

@@ -212,8 +212,16 @@ PC_HD void fwd_split(const float2* Z, float2* X, const float2* tw, int M, int k)
 // merge + pre-twist: W = Yt + (-1)^k Yp  (overlap-add done in the frequency domain: the second
 // half of IRFFT(Yp) equals the first half of IRFFT((-1)^k Yp)), then Z such that
 // IFFT_M(Z)[n] = x[2n] + i*x[2n+1].   k in [0, M/2].
-PC_HD float2 ola_merge(const float2* Yt, const float2* Yp, int M, int k) {
-  const float2 a = Yt[k], b = Yp[k];
+// np > 1 (multi-GPU slot exchange): row k of the spectrum is the sum of np partial rows that lie
+// `ps` float2 apart (one slot per contributing GPU)
+PC_HD float2 sum_partials(const float2* Y, int k, int np, long long ps) {
+  float2 a = Y[k];
+  for (int g = 1; g < np; ++g) { const float2 v = Y[(long long)g * ps + k]; a.x += v.x; a.y += v.y; }
+  return a;
+}
+
+PC_HD float2 ola_merge(const float2* Yt, const float2* Yp, int M, int k, int np, long long ps) {
+  const float2 a = sum_partials(Yt, k, np, ps), b = sum_partials(Yp, k, np, ps);
   if (k == 0) {
     const float s = (M & 1) ? -1.0f : 1.0f;             // Nyquist index M: (-1)^M
     return make_float2(a.x + b.x, a.y + s * b.y);
@@ -221,14 +229,14 @@ PC_HD float2 ola_merge(const float2* Yt, const float2* Yp, int M, int k) {
   return (k & 1) ? c_sub(a, b) : c_add(a, b);
 }
 
-PC_HD void inv_pre(const float2* Yt, const float2* Yp, float2* Z, const float2* tw, int M, int k) {
+PC_HD void inv_pre(const float2* Yt, const float2* Yp, float2* Z, const float2* tw, int M, int k, int np, long long ps) {
   if (k == 0) {
-    const float2 w0 = ola_merge(Yt, Yp, M, 0);
+    const float2 w0 = ola_merge(Yt, Yp, M, 0, np, ps);
     Z[swz(0)] = make_float2(0.5f * (w0.x + w0.y), 0.5f * (w0.x - w0.y));
     return;
   }
-  const float2 a = ola_merge(Yt, Yp, M, k);
-  const float2 b = c_conj(ola_merge(Yt, Yp, M, M - k));
+  const float2 a = ola_merge(Yt, Yp, M, k, np, ps);
+  const float2 b = c_conj(ola_merge(Yt, Yp, M, M - k, np, ps));
   const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
   const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
   const float2 O = c_mul(c_conj(tw[k]), D);
@@ -540,7 +548,32 @@ struct CmacParams {
   int B;
   int Ppad;                  // multiple of TT
   int nblocks;
+  // multi-GPU slot exchange (xg > 0): instead of Y, output block j is stored into the exchange
+  // buffer of the GPU that owns its time slice, in this GPU's slot:
+  //   owner o = min(xg-1, j / xper), row 1 + j - o*xper of xbase[o] + xrank*xslot   (row pitch y_rstride)
+  // the last block of slice o is also stored as row 0 (halo) of owner o+1, and block xhalo_block
+  // (last completed block of the group) into xhalo (owner 0's halo for the next group).
+  int xg, xrank, xper, xhalo_block;
+  long long xslot;
+  float2* xbase[8];
+  float2* xhalo;
 };
+
+
+// output store of the batched sweeps: plain Y row, or the multi-GPU slot exchange (CmacParams::xg > 0)
+PC_HD void cmac_store(const CmacParams& P, int c, int k, int j, float2 v) {
+  if (P.xg <= 0) {
+    P.Y[(long long)c * P.y_cstride + (P.yrow0 + j) * P.y_rstride + k] = v;
+    return;
+  }
+  int o = j / P.xper;
+  if (o > P.xg - 1) o = P.xg - 1;
+  const long long col = (long long)c * P.y_cstride + k;
+  const long long slot = (long long)P.xrank * P.xslot;
+  P.xbase[o][slot + (long long)(1 + j - o * P.xper) * P.y_rstride + col] = v;
+  if (o + 1 < P.xg && j == (o + 1) * P.xper - 1) P.xbase[o + 1][slot + col] = v;     // halo row of the next slice
+  if (j == P.xhalo_block) P.xhalo[(long long)P.xrank * P.y_rstride + col] = v;       // halo of the next group
+}
 
 struct InvParams {
   const float2* Y;           // block t of channel c: Y + c*y_cstride + (yrow0+t)*y_rstride; previous = one row before
@@ -551,6 +584,8 @@ struct InvParams {
   int M;
   int nblocks;
   float scale;               // 1/M
+  int n_partials;            // >= 1: every row is the sum of n_partials rows partial_stride apart (slot exchange)
+  long long partial_stride;
   // output
   float* dst; long long dst_cstride;
   long long index0;          // dst index of sample 0 of block 0
@@ -741,7 +776,7 @@ __global__ void __launch_bounds__(512) k_inv_fft_ola(InvParams P) {
     const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
     const float2* Yp = Yt - P.y_rstride;
 #pragma unroll 4
-    for (int k = tx; k <= M / 2; k += NT) inv_pre(Yt, Yp, bufA, tw, M, k);
+    for (int k = tx; k <= M / 2; k += NT) inv_pre(Yt, Yp, bufA, tw, M, k, P.n_partials, P.partial_stride);
   }
   fft_sync<WARP>();
   if constexpr (M == 1) {
@@ -764,10 +799,9 @@ __global__ void __launch_bounds__(32 * TW, MINB) k_cmac_batch2(CmacParams P) {
   const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
   float2 acc[TT];
   cmac_thread2<TT, D, BS>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
-  float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
 #pragma unroll
   for (int j = 0; j < TT; ++j)
-    if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
+    if (t0 + j < P.nblocks) cmac_store(P, c, k, t0 + j, acc[j]);
 }
 
 // grid (ceil(B/2/threads), nsplit, C), block (threads) with threads = min(256, B/2)
@@ -838,6 +872,36 @@ __global__ void __launch_bounds__(32 * PW) k_cmac_stream(StreamParams P) {
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross-GPU barrier over peer-mapped flag words (slot exchange).  One CTA, thread t < G:
+// publishes `epoch` in peer t's flag array at index `rank`, then waits until peer t has published
+// the same epoch here.  Flags only grow, so no reset is needed.  A bounded spin turns a lost peer
+// into an error word instead of a hung GPU.
+// ------------------------------------------------------------------------------------------
+struct BarrierParams {
+  unsigned int* peer_flags[8];   // flag array (8 words) of every rank, peer-mapped
+  unsigned int* my_flags;
+  unsigned int* error_word;      // set to epoch on timeout
+  int rank, G;
+  unsigned int epoch;
+};
+
+__global__ void k_p2p_barrier(BarrierParams P) {
+  const int t = threadIdx.x;
+  if (t >= P.G) return;
+  __threadfence_system();                      // everything this GPU wrote before the barrier is visible first
+  volatile unsigned int* out = P.peer_flags[t] + P.rank;
+  *out = P.epoch;
+  __threadfence_system();
+  volatile unsigned int* in = P.my_flags + t;
+  long long spins = 0;
+  while ((int)(*in - P.epoch) < 0) {
+    if (++spins > (1LL << 28)) { *P.error_word = P.epoch; break; }
+    __nanosleep(64);
+  }
+  __threadfence_system();
 }
 #endif  // __CUDACC__
 
@@ -918,9 +982,8 @@ inline void emu_cmac_batch2(EmuDim grid, const CmacParams& P) {
             const float2* Xk = P.X + (long long)c * P.x_cstride + (P.xrow0 + t0) * (long long)P.B + k;
             float2 acc[TT];
             cmac_thread2<TT, D>(Hk, Xk, P.B, P.Ppad, k == 0, acc);
-            float2* Yk = P.Y + (long long)c * P.y_cstride + (P.yrow0 + t0) * P.y_rstride + k;
             for (int j = 0; j < TT; ++j)
-              if (t0 + j < P.nblocks) Yk[(long long)j * P.y_rstride] = acc[j];
+              if (t0 + j < P.nblocks) cmac_store(P, c, k, t0 + j, acc[j]);
           }
 }
 
@@ -946,7 +1009,7 @@ inline void emu_inv_fft_ola(EmuDim grid, EmuDim block, const InvParams& P) {
         o.abs0 = P.abs0 + (long long)blk * M;
         const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
         const float2* Yp = Yt - P.y_rstride;
-        for (int k = 0; k <= M / 2; ++k) inv_pre(Yt, Yp, bufA, P.tw, M, k);
+        for (int k = 0; k <= M / 2; ++k) inv_pre(Yt, Yp, bufA, P.tw, M, k, P.n_partials, P.partial_stride);
         float2* in = bufA; float2* out = bufB;
         if (M == 1) {
           inv_store(in, M, P.scale, o, 0);

@@ -50,3 +50,13 @@ def attach_reduce(engine, device: int | None = None, group=None, root: int = 0) 
             dist.reduce(t, dst=root, op=dist.ReduceOp.SUM, group=group)
             return 0
     engine.set_reduce(hook)
+
+
+def attach_p2p(engine, group=None) -> None:
+    """Enables the fused slot-exchange path on a sharded uniform Engine: all-gathers the CUDA IPC
+    blobs of every rank with torch.distributed (plumbing only — the data path makes no NCCL call)."""
+    def allgather(blob: bytes):
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, blob, group=group)
+        return out
+    engine.p2p_attach(allgather, mode=0)

@@ -121,3 +121,59 @@ def test_sequential_fake_of_the_reduce(backend, G):
     o.init(128, h)
     yo = o.process(x)
     assert np.max(np.abs(outs - yo)) / np.max(np.abs(yo)) <= TOL
+
+
+def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_blocks=0):
+    """G shards of one convolver in G threads of this process (raw-pointer slot exchange)."""
+    import threading
+    lib_ = get_lib(lib_name)
+    gather_box, gather_bar = [None] * G, threading.Barrier(G)
+    host_bar = threading.Barrier(G)
+    outs, errs = [None] * G, []
+
+    def worker(rank):
+        try:
+            e = Engine(C, shard_rank=rank, shard_count=G, max_batch_blocks=max_batch_blocks, lib=lib_)
+            assert e.init_uniform(uniform_block, [ir] * C)
+
+            def allgather(blob):
+                gather_box[rank] = blob
+                gather_bar.wait(60)
+                res = list(gather_box)
+                gather_bar.wait(60)
+                return res
+            e.p2p_attach(allgather, mode=1, host_barrier=(lambda: (host_bar.wait(120), 0)[1]) if lib_name == "emu" else None)
+            ys, pos = [], 0
+            for k in chunks:
+                ys.append(e.process([x[pos:pos + k]] * C)[0])
+                pos += k
+            outs[rank] = np.concatenate(ys)
+            gather_bar.wait(120)      # nobody frees exchange buffers while a peer may still touch them
+            e.close()
+        except Exception as ex:      # pragma: no cover
+            errs.append(ex)
+            gather_bar.abort(); host_bar.abort()
+
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(600)
+    assert not errs, errs
+    return outs[0]
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("backend", ["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_slot_exchange_in_process(backend, G):
+    """Fused multi-GPU path with all shards in one process: sweep epilogue stores into the owners'
+    slots, flag/host barrier, per-slice inverse FFT summing the partial slots, audio gathered on shard 0."""
+    h = orc.synth_ir(9000)
+    n = 128 * 150 + 77
+    x = orc.synth_input(n)
+    o = orc.OracleUniform()
+    o.init(128, h)
+    yo = o.process(x)
+    for chunks in ([n], [5000, 128 * 40, 3, n - 5000 - 128 * 40 - 3], [128 * 50] * 3 + [77]):
+        y = _p2p_threads(backend, G, 128, h, x, chunks, max_batch_blocks=64)
+        assert np.max(np.abs(y - yo)) / np.max(np.abs(yo)) <= TOL, chunks

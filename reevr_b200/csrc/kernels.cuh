@@ -898,7 +898,7 @@ __global__ void k_p2p_barrier(BarrierParams P) {
   volatile unsigned int* in = P.my_flags + t;
   long long spins = 0;
   while ((int)(*in - P.epoch) < 0) {
-    if (++spins > (1LL << 28)) { *P.error_word = P.epoch; break; }
+    if (++spins > (1LL << 24)) { *P.error_word = P.epoch; break; }
     __nanosleep(64);
   }
   __threadfence_system();

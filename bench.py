@@ -37,6 +37,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware queue per stream: the engine's flag barriers spin on s_post while s_main keeps launching sweeps
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 B = 512
 SR = 48000

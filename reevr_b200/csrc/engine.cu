@@ -1077,7 +1077,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     for (int c = 0; c < C; ++c)
       CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
-    return B200CONV_OK;
+    return p2p_check(h);
   }
   // throughput path: H2D / compute / D2H of successive groups overlap on three streams
   size_t done = 0;
@@ -1108,7 +1108,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   CU_CHECK(h, cudaStreamSynchronize(h->s_out));
   if (int rc = join_post(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
-  return B200CONV_OK;
+  return p2p_check(h);
 }
 
 int b200conv_clear(b200conv_t* h) {

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# The in-process multi-shard tests run several handles (4 streams each) with spin-wait flag barriers on
+# ONE device: give every stream its own hardware queue so a spinning barrier cannot block a peer's kernels.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

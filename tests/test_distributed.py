@@ -163,8 +163,9 @@ def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_block
     return outs[0]
 
 
-@pytest.mark.parametrize("G", [2, 3, 8])
-@pytest.mark.parametrize("backend", ["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("backend,G", [("emu", 2), ("emu", 3), ("emu", 8),
+                                       pytest.param("cuda", 2, marks=pytest.mark.gpu),
+                                       pytest.param("cuda", 4, marks=pytest.mark.gpu)])
 def test_slot_exchange_in_process(backend, G):
     """Fused multi-GPU path with all shards in one process: sweep epilogue stores into the owners'
     slots, flag/host barrier, per-slice inverse FFT summing the partial slots, audio gathered on shard 0."""

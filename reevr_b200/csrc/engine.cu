@@ -659,6 +659,27 @@ int p2p_alloc(b200conv* h) {
   CU_CHECK(h, cudaMemsetAsync(h->Hh, 0, (size_t)3 * G * row * sizeof(float2), h->s_main));
   CU_CHECK(h, cudaMalloc(&h->xflags, 16 * sizeof(unsigned int)));
   CU_CHECK(h, cudaMemsetAsync(h->xflags, 0, 16 * sizeof(unsigned int), h->s_main));
+#if !defined(PC_EMULATE)
+  // Load every kernel / driver copy routine the exchange flow launches NOW: a lazy module load
+  // synchronises the context and must not happen while a peer's flag barrier is spinning on this device.
+  {
+    cudaFuncAttributes fa;
+    CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_p2p_barrier));
+#define PC_PRELOAD(BS) \
+    CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_cmac_batch2<16, 4, 4, BS, 3>)); \
+    CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_cmac_batch2<8, 4, 4, BS, 4>));
+    PC_PRELOAD(0) PC_PRELOAD(128) PC_PRELOAD(512) PC_PRELOAD(8192)
+#undef PC_PRELOAD
+    // strided device-to-device copies and memsets as used by run_group_p2p / compact_timeline
+    CU_CHECK(h, cudaMemcpy2DAsync(h->Yx[1], h->xslot * sizeof(float2), h->Hh, row * sizeof(float2), row * sizeof(float2), G,
+                                  cudaMemcpyDeviceToDevice, h->s_main));
+    CU_CHECK(h, cudaMemcpy2DAsync(h->xout[1], h->Lmax * sizeof(float), h->xout[0], h->Lmax * sizeof(float), sizeof(float), C,
+                                  cudaMemcpyDeviceToDevice, h->s_post));
+    CU_CHECK(h, cudaMemcpyAsync(h->Yx[1], h->Yx[0], row * sizeof(float2), cudaMemcpyDeviceToDevice, h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(h->Yx[1], 0, (size_t)G * h->xslot * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaStreamSynchronize(h->s_post));
+  }
+#endif
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return 0;
 }

@@ -4,6 +4,9 @@ import sys
 # The in-process multi-shard tests run several handles (4 streams each) with spin-wait flag barriers on
 # ONE device: give every stream its own hardware queue so a spinning barrier cannot block a peer's kernels.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and load all kernels up front: a lazy module load synchronises the context and would dead-lock against
+# another in-process shard's spinning barrier (not an issue with one process per GPU).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import pytest
 

@@ -705,6 +705,13 @@ int p2p_barrier(b200conv* h, cudaStream_t st) {
   if (!h->host_barrier) return fail(h, B200CONV_ESTATE, "emulated slot exchange needs a host barrier");
   if (h->host_barrier(h->host_barrier_user) != 0) return fail(h, B200CONV_ECUDA, "host barrier failed");
 #else
+  if (h->host_barrier) {
+    // all shards in ONE process on one device (tests): spinning flag kernels of several handles share the
+    // device's hardware queues / copy engines and can block each other, so synchronise through the host
+    CU_CHECK(h, cudaStreamSynchronize(st));
+    if (h->host_barrier(h->host_barrier_user) != 0) return fail(h, B200CONV_ECUDA, "host barrier failed");
+    return 0;
+  }
   pc::BarrierParams bp{};
   for (int g = 0; g < h->cfg.shard_count; ++g) bp.peer_flags[g] = h->peer_flags[g];
   bp.my_flags = h->xflags;

@@ -142,7 +142,10 @@ def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_block
                 res = list(gather_box)
                 gather_bar.wait(60)
                 return res
-            e.p2p_attach(allgather, mode=1, host_barrier=(lambda: (host_bar.wait(120), 0)[1]) if lib_name == "emu" else None)
+            # in-process shards synchronise through the host (emulation has no device barrier; on one GPU
+            # several spinning flag kernels would block each other through the shared hardware queues) —
+            # the flag kernel itself is exercised by the multi-process multi-GPU runs of bench.py
+            e.p2p_attach(allgather, mode=1, host_barrier=lambda: (host_bar.wait(120), 0)[1])
             ys, pos = [], 0
             for k in chunks:
                 ys.append(e.process([x[pos:pos + k]] * C)[0])

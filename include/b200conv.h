@@ -109,6 +109,15 @@ void*  b200conv_stream(const b200conv_t* h);                  /* cudaStream_t of
 typedef int (*b200conv_reduce_fn)(void* user, float* dev_buf, size_t n_floats, void* cuda_stream);
 int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
 
+/* Optional I/O routing of a multi-convolver handle (StereoConvolver as ONE call incl.
+ * the true-stereo mixdown of src/PluginProcessor.cpp:1833-1838).  Convolver c reads input buffer
+ * in_map[c] (0 <= in_map[c] < n_in) and output o = sum_c mix[o*C + c] * y_c, computed on the device.
+ * Afterwards b200conv_process / b200conv_process_device take n_in input and n_out output buffers
+ * (e.g. quad reverb: in = {L, R}, convolvers {LL, RR, LR, RL} <- {0, 1, 0, 1}, out L = LL + RL,
+ * out R = RR + LR: 2 buffers each way over PCIe instead of 4).  n_in = 0 removes the routing.
+ * Limits: C <= 8, n_in <= 8, n_out <= 8; not combinable with the slot exchange. */
+int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, const float* mix);
+
 /* Fused multi-GPU path ("slot exchange", uniform single-stage handles with shard_count > 1):
  * the sweep kernel's epilogue stores each partial spectrum row straight into the exchange buffer of
  * the GPU that owns the row's time slice (peer memory over NVLink), a flag barrier follows, every

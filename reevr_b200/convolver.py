@@ -76,9 +76,11 @@ class Engine:
         """xs: C arrays of equal length (host). Returns C float32 arrays."""
         xs = [np.ascontiguousarray(a, dtype=np.float32) for a in xs]
         n = xs[0].size
-        if any(a.size != n for a in xs) or len(xs) != self.n_channels:
-            raise ValueError("need one equally long input per channel")
-        ys = [np.empty(max(n, 1), np.float32)[:n] for _ in xs]
+        n_in = getattr(self, "_n_in", None) or self.n_channels
+        n_out = getattr(self, "_n_out", None) or self.n_channels
+        if any(a.size != n for a in xs) or len(xs) != n_in:
+            raise ValueError("need one equally long input per (routed) input channel")
+        ys = [np.empty(max(n, 1), np.float32)[:n] for _ in range(n_out)]
         if n:
             self._check(self._l.b200conv_process(self._h, _ptr_array(xs), _ptr_array(ys), n), "process")
         return ys
@@ -137,6 +139,22 @@ class Engine:
                 return -1
         self._reduce_cb = _lib.REDUCE_FN(tramp)
         self._l.b200conv_set_reduce(self._h, self._reduce_cb, None)
+
+    def set_routing(self, in_map, mix):
+        """Convolver c reads input in_map[c]; output o = sum_c mix[o][c] * y_c (computed on the device).
+        `mix` is an (n_out, C) array.  set_routing(None, None) removes the routing."""
+        if in_map is None:
+            self._check(self._l.b200conv_set_routing(self._h, 0, None, 0, None), "set_routing")
+            self._n_in = self._n_out = None
+            return
+        mix = np.ascontiguousarray(mix, dtype=np.float32)
+        n_out, Cc = mix.shape
+        assert Cc == self.n_channels and len(in_map) == self.n_channels
+        n_in = max(in_map) + 1
+        im = (C.c_int * Cc)(*in_map)
+        self._check(self._l.b200conv_set_routing(self._h, n_in, im, n_out,
+                                                 mix.ctypes.data_as(C.POINTER(C.c_float))), "set_routing")
+        self._n_in, self._n_out = n_in, n_out
 
     def p2p_attach(self, allgather, mode: int = 0, host_barrier=None):
         """Enables the fused multi-GPU path (slot exchange over peer memory, see b200conv.h).
@@ -228,6 +246,19 @@ class StereoConvolver:
         """Returns (bufferLL, bufferRR[, bufferLR, bufferRL])."""
         xs = [dataL, dataR] + ([dataL, dataR] if self.isQuad else [])
         return tuple(self._e.process(xs))
+
+    def enable_device_mixdown(self, true_stereo: bool = True):
+        """feed {L, R} once and get the wet {L, R} back, mixed on the device as
+        src/PluginProcessor.cpp:1833-1838 does on the host (L = LL + RL, R = RR + LR when quad & true stereo)."""
+        if self.isQuad:
+            ts = 1.0 if true_stereo else 0.0
+            self._e.set_routing([0, 1, 0, 1], [[1, 0, 0, ts], [0, 1, ts, 0]])
+        else:
+            self._e.set_routing([0, 1], [[1, 0], [0, 1]])
+
+    def process_mixed(self, dataL, dataR):
+        """(wetL, wetR) after enable_device_mixdown()."""
+        return tuple(self._e.process([dataL, dataR]))
 
     def clear(self):
         if self._e:

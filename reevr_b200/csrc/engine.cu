@@ -102,6 +102,12 @@ struct b200conv {
   b200conv_reduce_fn reduce = nullptr;
   void* reduce_user = nullptr;
   int n_sm = 148;
+  // I/O routing + mixdown (b200conv_set_routing)
+  bool route_on = false;
+  int n_in = 0, n_out = 0;
+  int in_map[8] = {};
+  float mix[64] = {};
+  float* dch[2] = {nullptr, nullptr};       // per-convolver outputs [C][Lmax] before the mixdown
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -160,8 +166,8 @@ void free_all(b200conv* h) {
   for (auto& s : h->stages) free_stage(s);
   h->stages.clear();
   for (int i = 0; i < 2; ++i) {
-    cudaFree(h->din[i]); cudaFree(h->dout[i]);
-    h->din[i] = h->dout[i] = nullptr;
+    cudaFree(h->din[i]); cudaFree(h->dout[i]); cudaFree(h->dch[i]);
+    h->din[i] = h->dout[i] = h->dch[i] = nullptr;
   }
   h->ir_len.assign(h->C, 0);
   h->abs_pos = 0;
@@ -620,10 +626,61 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
   for (int i = 0; i < 2; ++i) {
     CU_CHECK(h, cudaMalloc(&h->din[i], (size_t)C * h->Lmax * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&h->dout[i], (size_t)C * h->Lmax * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&h->dch[i], (size_t)C * h->Lmax * sizeof(float)));
   }
   if (int rc = clear_state(h)) { free_all(h); return rc; }
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return B200CONV_OK;
+}
+
+// copies `count` samples of every convolver channel from the caller's device buffer (n_in routed inputs or
+// C plain channels) into a C-channel staging buffer
+int copy_in(b200conv* h, float* dst, size_t dstride, const float* src, size_t sstride, size_t count) {
+  if (count == 0) return 0;
+  if (!h->route_on) {
+    CU_CHECK(h, cudaMemcpy2DAsync(dst, dstride * sizeof(float), src, sstride * sizeof(float), count * sizeof(float), h->C,
+                                  cudaMemcpyDeviceToDevice, h->s_main));
+  } else {
+    for (int c = 0; c < h->C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(dst + (size_t)c * dstride, src + (size_t)h->in_map[c] * sstride, count * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, h->s_main));
+  }
+  return 0;
+}
+
+void set_cmap(const b200conv* h, pc::FwdParams& fp, bool direct) {
+  fp.use_cmap = (direct && h->route_on) ? 1 : 0;
+  for (int c = 0; c < 8; ++c) fp.cmap[c] = h->in_map[c];
+}
+
+#if !defined(PC_EMULATE)
+#define PC_LAUNCH_MIX(mp, grid, st) pc::k_mix<<<grid, 256, 0, st>>>(mp)
+#endif
+
+// per-convolver outputs (C channels in `in`) -> n_out mixed outputs
+int launch_mix(b200conv* h, const float* in, size_t in_stride, float* out, size_t out_stride, size_t n, cudaStream_t st) {
+#if defined(PC_EMULATE)
+  (void)st;
+  for (int o = 0; o < h->n_out; ++o)
+    for (size_t i = 0; i < n; ++i) {
+      float acc = 0.0f;
+      for (int c = 0; c < h->C; ++c) {
+        const float m = h->mix[o * h->C + c];
+        if (m != 0.0f) acc = std::fmaf(m, in[(size_t)c * in_stride + i], acc);
+      }
+      out[(size_t)o * out_stride + i] = acc;
+    }
+#else
+  pc::MixParams mp{};
+  mp.in = in; mp.in_stride = (long long)in_stride; mp.out = out; mp.out_stride = (long long)out_stride;
+  mp.n = (long long)n; mp.C = h->C; mp.n_out = h->n_out;
+  std::memcpy(mp.mix, h->mix, sizeof(mp.mix));
+  dim3 grid((unsigned)((n + 255) / 256), h->n_out, 1);
+  PC_LAUNCH_MIX(mp, grid, st);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+#endif
+  return 0;
 }
 
 // ---- one launch group: n <= Lmax samples, device-resident ------------------------------------
@@ -815,7 +872,10 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
               bool overlap) {
   const int C = h->C;
   const bool root = h->cfg.shard_rank == 0;
-  if (h->p2p_on) return run_group_p2p(h, in_dev, in_stride, out_dev, out_stride, n);
+  if (h->p2p_on) {
+    if (h->route_on) return fail(h, B200CONV_ESTATE, "I/O routing is not available on the slot-exchange path");
+    return run_group_p2p(h, in_dev, in_stride, out_dev, out_stride, n);
+  }
   cudaStream_t ps = overlap ? h->s_post : h->s_main;
   if (n == 0) return 0;
   if (n + h->stages[0].B > h->Lmax) return fail(h, B200CONV_ESTATE, "launch group larger than the staging buffers");
@@ -831,9 +891,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
     // With an empty open block the forward FFT reads the caller's buffer directly; only a trailing
     // partial block is buffered.  Otherwise the new samples are appended behind the open block's.
     const bool direct = (s.fill == 0);
-    if (!direct)
-      CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf + s.fill, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
-                                    n * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+    if (!direct) { if (int rc = copy_in(h, s.inbuf + s.fill, s.in_stride, in_dev, in_stride, n)) return rc; }
     const int yb = s.ybuf;
     float2* Yb = s.Y[yb];
     if (nb > 0) {
@@ -842,6 +900,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
       fp.src = direct ? in_dev : s.inbuf;
       fp.src_cstride = direct ? (long long)in_stride : (long long)s.in_stride;
       fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
+      set_cmap(h, fp, direct);
       fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
       fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
       if (int rc = launch_fwd(h, fp, C)) return rc;
@@ -869,7 +928,8 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
         ip.Y = Yb; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
         ip.tw = s.tw; ip.M = B; ip.nblocks = nb; ip.scale = 1.0f / (float)B;
         if (si == 0) {
-          ip.dst = out_dev; ip.dst_cstride = (long long)out_stride;
+          ip.dst = h->route_on ? h->dch[0] : out_dev;
+          ip.dst_cstride = h->route_on ? (long long)h->Lmax : (long long)out_stride;
           ip.index0 = -(long long)s.fill; ip.lo = 0; ip.hi = (long long)n; ip.mask = -1;
           ip.abs0 = h->abs_pos - s.fill;
           int na = 0;
@@ -886,6 +946,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
           ip.n_add = 0; ip.abs0 = 0;
         }
         if (int rc = launch_inv(h, ip, C, ps)) return rc;
+        if (si == 0 && h->route_on) { if (int rc = launch_mix(h, h->dch[0], h->Lmax, out_dev, out_stride, n, ps)) return rc; }
       }
     }
     // state update
@@ -897,17 +958,17 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
       if (overlap) CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
       s.ybuf = nxt;
       if (partial > 0) {
-        const float* tail_src = direct ? in_dev + (size_t)complete * B : s.inbuf + (size_t)complete * B;
-        const size_t tail_pitch = direct ? in_stride : s.in_stride;
-        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), tail_src, tail_pitch * sizeof(float),
-                                      partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+        if (direct) { if (int rc = copy_in(h, s.inbuf, s.in_stride, in_dev + (size_t)complete * B, in_stride, partial)) return rc; }
+        else
+          CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), s.inbuf + (size_t)complete * B,
+                                        s.in_stride * sizeof(float), partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
       }
       s.head += complete;
       s.blocks_done += complete;
     } else {
-      if (direct && partial > 0)     // nothing completed: keep the partial block's samples for the next call
-        CU_CHECK(h, cudaMemcpy2DAsync(s.inbuf, s.in_stride * sizeof(float), in_dev, in_stride * sizeof(float),
-                                      partial * sizeof(float), C, cudaMemcpyDeviceToDevice, h->s_main));
+      if (direct && partial > 0) {   // nothing completed: keep the partial block's samples for the next call
+        if (int rc = copy_in(h, s.inbuf, s.in_stride, in_dev, in_stride, partial)) return rc;
+      }
       if (overlap && nb > 0) CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
     }
     s.fill = partial;
@@ -1062,7 +1123,8 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
   if (int rc = set_device(h)) return rc;
   if (h->timing) h->ev_used = 0;
   if (h->stages.empty()) {      // no IR: zeros (FFTConvolver.cpp:157-161)
-    if (len) CU_CHECK(h, cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, len * sizeof(float), h->C, h->s_main));
+    if (len) CU_CHECK(h, cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, len * sizeof(float),
+                                           h->route_on ? h->n_out : h->C, h->s_main));
   } else {
     const size_t B0 = h->stages[0].B;
     const size_t chunk = h->Lmax - B0;     // keeps fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
@@ -1089,20 +1151,21 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   if (!in || !out) return fail(h, B200CONV_EINVAL, "null buffer");
   if (int rc = set_device(h)) return rc;
   const int C = h->C;
+  const int Cin = h->route_on ? h->n_in : C, Cout = h->route_on ? h->n_out : C;
   if (h->stages.empty()) {
-    for (int c = 0; c < C; ++c) std::memset(out[c], 0, len * sizeof(float));
+    for (int c = 0; c < Cout; ++c) std::memset(out[c], 0, len * sizeof(float));
     return B200CONV_OK;
   }
   const size_t B0 = h->stages[0].B;
   const size_t chunk = h->Lmax - B0;
   if (len <= chunk && len <= std::max((size_t)64 * B0, (size_t)16384)) {
     // latency path: one stream, one group
-    for (int c = 0; c < C; ++c)
+    for (int c = 0; c < Cin; ++c)
       CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
     const bool ov = h->cfg.shard_count > 1;
     if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len, ov)) return rc;
     if (ov) { if (int rc = join_post(h)) return rc; }
-    for (int c = 0; c < C; ++c)
+    for (int c = 0; c < Cout; ++c)
       CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
     return p2p_check(h);
@@ -1119,7 +1182,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     const int b = i & 1;
     const size_t n = std::min(len - done, grp);
     if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_din[b], 0));     // din[b] free again
-    for (int c = 0; c < C; ++c)
+    for (int c = 0; c < Cin; ++c)
       CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * h->Lmax, in[c] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
     CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
     CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_h2d[b], 0));
@@ -1128,7 +1191,7 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     CU_CHECK(h, cudaEventRecord(h->ev_din[b], h->s_main));    // every read of din[b] is queued on s_main
     CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_post));    // dout[b] complete
     CU_CHECK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
-    for (int c = 0; c < C; ++c)
+    for (int c = 0; c < Cout; ++c)
       CU_CHECK(h, cudaMemcpyAsync(out[c] + done, h->dout[b] + (size_t)c * h->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
     CU_CHECK(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
     done += n;
@@ -1193,6 +1256,23 @@ void* b200conv_stream(const b200conv_t* h) { return h ? (void*)h->s_main : nullp
 int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user) {
   if (!h) return B200CONV_EINVAL;
   h->reduce = fn; h->reduce_user = user;
+  return B200CONV_OK;
+}
+
+int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, const float* mix) {
+  if (!h) return B200CONV_EINVAL;
+  if (n_in == 0) { h->route_on = false; return B200CONV_OK; }
+  const int C = h->C;
+  if (C > 8 || n_in < 1 || n_in > C || n_out < 1 || n_out > C || !in_map || !mix)
+    return fail(h, B200CONV_EINVAL, "routing needs C <= 8, 1 <= n_in, n_out <= C, in_map[C] and mix[n_out*C]");
+  for (int c = 0; c < C; ++c)
+    if (in_map[c] < 0 || in_map[c] >= n_in) return fail(h, B200CONV_EINVAL, "in_map entry out of range");
+  if (h->s_main) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->s_main); if (h->s_post) cudaStreamSynchronize(h->s_post); }
+  h->n_in = n_in; h->n_out = n_out;
+  for (int c = 0; c < 8; ++c) h->in_map[c] = c < C ? in_map[c] : 0;
+  std::memset(h->mix, 0, sizeof(h->mix));
+  for (int i = 0; i < n_out * C; ++i) h->mix[i] = mix[i];
+  h->route_on = true;
   return B200CONV_OK;
 }
 

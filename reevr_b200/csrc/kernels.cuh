@@ -216,7 +216,13 @@ PC_HD void fwd_split(const float2* Z, float2* X, const float2* tw, int M, int k)
 // `ps` float2 apart (one slot per contributing GPU)
 PC_HD float2 sum_partials(const float2* Y, int k, int np, long long ps) {
   float2 a = Y[k];
-  for (int g = 1; g < np; ++g) { const float2 v = Y[(long long)g * ps + k]; a.x += v.x; a.y += v.y; }
+  if (np > 1) {
+    float2 v[7];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) v[g - 1] = g < np ? Y[(long long)g * ps + k] : make_float2(0.f, 0.f);   // loads first
+#pragma unroll
+    for (int g = 0; g < 7; ++g) { a.x += v[g].x; a.y += v[g].y; }
+  }
   return a;
 }
 
@@ -533,6 +539,8 @@ struct FwdParams {
   const float2* tw;
   int M;                     // = B
   int nblocks;
+  int use_cmap;              // routing: channel c reads source channel cmap[c] (StereoConvolver: LL,RR,LR,RL <- L,R,L,R)
+  int cmap[8];
 };
 
 struct CmacParams {
@@ -692,7 +700,7 @@ __global__ void __launch_bounds__(512) k_fwd_fft(FwdParams P) {
     const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
     long long rem = nv_total - (long long)blk * M;
     nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
-    src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
+    src = P.src + (long long)(P.use_cmap ? P.cmap[c] : c) * P.src_cstride + (long long)blk * M;
   }
   float2* res = bufA;
   if constexpr (M == 1) {
@@ -903,6 +911,28 @@ __global__ void k_p2p_barrier(BarrierParams P) {
   }
   __threadfence_system();
 }
+
+// out[o][i] = sum_c mix[o*C + c] * in[c][i]   (true-stereo mixdown of the per-convolver outputs,
+// src/PluginProcessor.cpp:1833-1838: wet L = LL + RL, wet R = RR + LR); grid (ceil(n/256), n_out)
+struct MixParams {
+  const float* in; long long in_stride;
+  float* out; long long out_stride;
+  long long n;
+  int C, n_out;
+  float mix[64];
+};
+
+__global__ void k_mix(MixParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y;
+  if (i >= P.n) return;
+  float acc = 0.0f;
+  for (int c = 0; c < P.C; ++c) {
+    const float m = P.mix[o * P.C + c];
+    if (m != 0.0f) acc = fmaf(m, P.in[(long long)c * P.in_stride + i], acc);
+  }
+  P.out[(long long)o * P.out_stride + i] = acc;
+}
 #endif  // __CUDACC__
 
 
@@ -926,7 +956,7 @@ inline void emu_fwd_fft(EmuDim grid, EmuDim block, const FwdParams& P) {
         const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
         long long rem = nv_total - (long long)blk * M;
         const int nv = rem <= 0 ? 0 : (rem > M ? M : (int)rem);
-        const float* src = P.src + (long long)c * P.src_cstride + (long long)blk * M;
+        const float* src = P.src + (long long)(P.use_cmap ? P.cmap[c] : c) * P.src_cstride + (long long)blk * M;
         float2* in = bufA; float2* out = bufB;
         if (M == 1) {
           fwd_load(src, nv, in, M, 0);

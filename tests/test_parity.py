@@ -254,3 +254,40 @@ def test_cmac_variants(lib, variant):
     o = orc.OracleUniform()
     o.init(64, h)
     assert peak_err(y, o.run(x, 64)) <= TOL
+
+
+def test_device_mixdown_quad(lib):
+    """StereoConvolver quad as ONE call with 2 inputs / 2 outputs and the true-stereo
+    mixdown on the device (src/PluginProcessor.cpp:1833-1838: wet L = LL + RL, wet R = RR + LR)."""
+    sc = StereoConvolver(lib=lib)
+    sc.prepare(100)                                    # head 128, tail 8192
+    irs = [orc.synth_ir(20000, c) for c in range(4)]   # LL, RR, LR, RL
+    sc.loadImpulse(*irs)
+    sc.enable_device_mixdown(true_stereo=True)
+    n = 100 * 40
+    L, R = orc.synth_input(n, 0), orc.synth_input(n, 1)
+    wl, wr = np.empty_like(L), np.empty_like(R)
+    for i in range(40):
+        seg = slice(100 * i, 100 * (i + 1))
+        wl[seg], wr[seg] = sc.process_mixed(L[seg], R[seg])
+    outs = []
+    for ir, src in zip(irs, (L, R, L, R)):
+        o = orc.OracleTwoStage()
+        o.init(128, 8192, ir)
+        outs.append(run_chunks(o, src, [100] * 40))
+    LL, RR, LR, RL = outs
+    assert peak_err(wl, LL + RL) <= TOL
+    assert peak_err(wr, RR + LR) <= TOL
+    # long call through the pipelined path + removing the routing again
+    e = Engine(4, lib=lib, max_batch_blocks=32)
+    assert e.init_uniform(64, [ir[:3000] for ir in irs])
+    e.set_routing([0, 1, 0, 1], [[1, 0, 0, 1], [0, 1, 1, 0]])
+    yl, yr = e.process([L, R])
+    refs = []
+    for ir, src in zip(irs, (L, R, L, R)):
+        o = orc.OracleUniform()
+        o.init(64, ir[:3000])
+        refs.append(o.process(src))
+    assert peak_err(yl, refs[0] + refs[3]) <= TOL and peak_err(yr, refs[1] + refs[2]) <= TOL
+    e.set_routing(None, None)
+    assert len(e.process([L[:64], R[:64], L[:64], R[:64]])) == 4

@@ -1173,10 +1173,15 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   // throughput path: H2D / compute / D2H of successive groups overlap on three streams
   size_t done = 0;
   int i = 0;
-  // split long calls into ~3 groups so that the PCIe copies overlap with compute; group length is a
-  // multiple of 64 blocks (= one sweep tile of 4 warps x 16 blocks) to keep the sweep grid wave-aligned
+  // Split long calls into groups so that the PCIe copies overlap with compute: only the first group's H2D
+  // and the last group's D2H are exposed, so aim for ~8 groups — but keep every group a whole number of
+  // sweep WAVES (n_sm x 3 CTAs x 64 blocks per CTA over ceil(B/32) x C tile columns), otherwise a
+  // partially filled last wave costs more than the overlap gains.
   const size_t tile = (size_t)B0 * 64;
-  size_t grp = ((len + 2) / 3 + tile - 1) / tile * tile;
+  const size_t cols = (size_t)((B0 + 31) / 32) * (size_t)h->C;
+  size_t wave = ((size_t)h->n_sm * 3 * 64 + cols - 1) / cols * (size_t)B0;       // samples per full wave
+  wave = std::max(tile, wave / tile * tile);
+  size_t grp = std::max(wave, (len / 8) / wave * wave);
   grp = std::min(grp, chunk >= tile ? chunk / tile * tile : chunk);
   for (; done < len; ++i) {
     const int b = i & 1;

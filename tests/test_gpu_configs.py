@@ -151,3 +151,36 @@ def test_device_resident_batch_matches_host_path():
     y = y.cpu().numpy()
     for c in range(2):
         assert peak_err(y[c], yh[c]) <= 1e-7
+
+
+def test_cfg3_true_nonuniform_schedule():
+    """Config 3 with a real non-uniform partition schedule (64 / 512 / 4096 / 8192 — beyond the
+    reference): same linear convolution, checked against the reference's
+    two-stage output on seeded noise and against the impulse identity over the whole 30 s IR."""
+    L = 96000 * 30
+    irs = [synth_ir(L, c) for c in range(2)]
+    blocks, offsets = [64, 512, 4096, 8192], [0, 1024, 8192, 65536]
+    e = Engine(2)
+    assert e.init_stages(blocks, offsets, irs)
+    assert [s["block"] for s in e.stages()] == blocks
+    n = 64 * 700
+    xs = [synth_input(n, c) for c in range(2)]
+    ys = [np.empty(n, np.float32) for _ in range(2)]
+    pos = 0
+    for k in [64 * 300, 48, 48, 5000, n - 64 * 300 - 96 - 5000]:
+        for c, y in enumerate(e.process([x[pos:pos + k] for x in xs])):
+            ys[c][pos:pos + k] = y
+        pos += k
+    o = _oracle_cls("twostage")()
+    assert o.init(64, 8192, irs[0])
+    assert peak_err(ys[0], o.run(xs[0], 64)) <= TOL
+    # impulse -> IR over all four stages
+    e2 = Engine(1)
+    assert e2.init_stages(blocks, offsets, [irs[1]])
+    d = 333
+    x = np.zeros(L + d + 100, np.float32)
+    x[d] = 1.0
+    y = e2.process([x])[0]
+    want = np.zeros_like(x)
+    want[d:d + e2.ir_len(0)] = irs[1][:e2.ir_len(0)]
+    assert peak_err(y, want) <= TOL

@@ -118,6 +118,17 @@ int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
  * Limits: C <= 8, n_in <= 8, n_out <= 8; not combinable with the slot exchange. */
 int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, const float* mix);
 
+/* IR hot-swap helpers (the reference replays a 0.25 s "warmer" ring through the freshly
+ * loaded convolver call by call and crossfades two convolvers on the host for 50 ms,
+ * src/PluginProcessor.cpp:1695-1750,1800-1830).
+ * b200conv_prime: feeds `len` samples of history through the handle in ONE batched call, no output.
+ * b200conv_process_xfade: runs both handles on the same input and returns
+ *   out[c][i] = (1 - a_i) * old[c][i] + a_i * new[c][i],  a_i = clamp(alpha0 + i*alpha_step, 0, 1),
+ *   blended on the device (one D2H).  Both handles: same device, same channel count / routing, unsharded. */
+int b200conv_prime(b200conv_t* h, const float* const* in, size_t len);
+int b200conv_process_xfade(b200conv_t* h_old, b200conv_t* h_new, const float* const* in, float* const* out,
+                           size_t len, float alpha0, float alpha_step);
+
 /* Fused multi-GPU path ("slot exchange", uniform single-stage handles with shard_count > 1):
  * the sweep kernel's epilogue stores each partial spectrum row straight into the exchange buffer of
  * the GPU that owns the row's time slice (peer memory over NVLink), a flag barrier follows, every

@@ -85,6 +85,25 @@ class Engine:
             self._check(self._l.b200conv_process(self._h, _ptr_array(xs), _ptr_array(ys), n), "process")
         return ys
 
+    def prime(self, xs) -> None:
+        """Feeds history through the convolver in one batched call without producing output
+        (IR hot-swap warm-up, src/PluginProcessor.cpp:1695-1750)."""
+        xs = [np.ascontiguousarray(a, dtype=np.float32) for a in xs]
+        if xs[0].size:
+            self._check(self._l.b200conv_prime(self._h, _ptr_array(xs), xs[0].size), "prime")
+
+    def process_xfade(self, new: "Engine", xs, alpha0: float, alpha_step: float) -> list:
+        """self = outgoing convolver, `new` = incoming one: device-side crossfade of both outputs
+        (src/PluginProcessor.cpp:1800-1830)."""
+        xs = [np.ascontiguousarray(a, dtype=np.float32) for a in xs]
+        n = xs[0].size
+        n_out = getattr(self, "_n_out", None) or self.n_channels
+        ys = [np.empty(max(n, 1), np.float32)[:n] for _ in range(n_out)]
+        if n:
+            self._check(self._l.b200conv_process_xfade(self._h, new._h, _ptr_array(xs), _ptr_array(ys), n,
+                                                       alpha0, alpha_step), "process_xfade")
+        return ys
+
     def process_into(self, in_ptrs, out_ptrs, n: int) -> None:
         """Raw host pointers (ctypes arrays of void*), e.g. pinned staging buffers."""
         self._check(self._l.b200conv_process(self._h, in_ptrs, out_ptrs, n), "process")

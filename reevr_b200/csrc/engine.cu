@@ -1145,15 +1145,15 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
   return B200CONV_OK;
 }
 
-int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, size_t len) {
+static int process_impl(b200conv_t* h, const float* const* in, float* const* out, size_t len) {
   REQUIRE_CUDA(h);
   if (len == 0) return B200CONV_OK;
-  if (!in || !out) return fail(h, B200CONV_EINVAL, "null buffer");
+  if (!in) return fail(h, B200CONV_EINVAL, "null buffer");
   if (int rc = set_device(h)) return rc;
   const int C = h->C;
   const int Cin = h->route_on ? h->n_in : C, Cout = h->route_on ? h->n_out : C;
   if (h->stages.empty()) {
-    for (int c = 0; c < Cout; ++c) std::memset(out[c], 0, len * sizeof(float));
+    if (out) for (int c = 0; c < Cout; ++c) std::memset(out[c], 0, len * sizeof(float));
     return B200CONV_OK;
   }
   const size_t B0 = h->stages[0].B;
@@ -1165,8 +1165,9 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     const bool ov = h->cfg.shard_count > 1;
     if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len, ov)) return rc;
     if (ov) { if (int rc = join_post(h)) return rc; }
-    for (int c = 0; c < Cout; ++c)
-      CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    if (out)
+      for (int c = 0; c < Cout; ++c)
+        CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
     return p2p_check(h);
   }
@@ -1196,8 +1197,9 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
     CU_CHECK(h, cudaEventRecord(h->ev_din[b], h->s_main));    // every read of din[b] is queued on s_main
     CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_post));    // dout[b] complete
     CU_CHECK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
-    for (int c = 0; c < Cout; ++c)
-      CU_CHECK(h, cudaMemcpyAsync(out[c] + done, h->dout[b] + (size_t)c * h->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (out)
+      for (int c = 0; c < Cout; ++c)
+        CU_CHECK(h, cudaMemcpyAsync(out[c] + done, h->dout[b] + (size_t)c * h->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
     CU_CHECK(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
     done += n;
   }
@@ -1205,6 +1207,71 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
   if (int rc = join_post(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return p2p_check(h);
+}
+
+int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, size_t len) {
+  if (h && len && !out) return fail(h, B200CONV_EINVAL, "null buffer");
+  return process_impl(h, in, out, len);
+}
+
+int b200conv_prime(b200conv_t* h, const float* const* in, size_t len) { return process_impl(h, in, nullptr, len); }
+
+int b200conv_process_xfade(b200conv_t* ho, b200conv_t* hn, const float* const* in, float* const* out,
+                           size_t len, float alpha0, float alpha_step) {
+  REQUIRE_CUDA(ho);
+  REQUIRE_CUDA(hn);
+  if (len == 0) return B200CONV_OK;
+  if (!in || !out) return fail(hn, B200CONV_EINVAL, "null buffer");
+  if (ho == hn || ho->cfg.device != hn->cfg.device || ho->C != hn->C || ho->route_on != hn->route_on ||
+      (ho->route_on && (ho->n_in != hn->n_in || ho->n_out != hn->n_out)) ||
+      ho->cfg.shard_count > 1 || hn->cfg.shard_count > 1)
+    return fail(hn, B200CONV_EINVAL, "crossfade needs two different unsharded handles with the same device, channels and routing");
+  if (int rc = set_device(hn)) return rc;
+  const int C = hn->C;
+  const int Cin = hn->route_on ? hn->n_in : C, Cout = hn->route_on ? hn->n_out : C;
+  if (ho->stages.empty() || hn->stages.empty()) {   // one side has no IR: its output is silence
+    b200conv_t* live = ho->stages.empty() ? hn : ho;
+    if (int rc = process_impl(live, in, out, len)) return rc;
+    for (int c = 0; c < Cout; ++c)
+      for (size_t i = 0; i < len; ++i) {
+        const float al = std::fmin(1.0f, std::fmax(0.0f, alpha0 + alpha_step * (float)i));
+        out[c][i] *= (live == hn) ? al : (1.0f - al);
+      }
+    return B200CONV_OK;
+  }
+  const size_t chunk = std::min(ho->Lmax - ho->stages[0].B, hn->Lmax - hn->stages[0].B);
+  for (size_t done = 0; done < len;) {
+    const size_t n = std::min(len - done, chunk);
+    // input once (old handle's staging), both convolvers read it
+    for (int c = 0; c < Cin; ++c)
+      CU_CHECK(ho, cudaMemcpyAsync(ho->din[0] + (size_t)c * ho->Lmax, in[c] + done, n * sizeof(float), cudaMemcpyHostToDevice, ho->s_main));
+    CU_CHECK(ho, cudaEventRecord(ho->ev_h2d[0], ho->s_main));
+    if (int rc = run_group(ho, ho->din[0], ho->Lmax, ho->dout[0], ho->Lmax, n, false)) return rc;
+    CU_CHECK(ho, cudaEventRecord(ho->ev_comp[0], ho->s_main));
+    CU_CHECK(hn, cudaStreamWaitEvent(hn->s_main, ho->ev_h2d[0], 0));
+    if (int rc = run_group(hn, ho->din[0], ho->Lmax, hn->dout[0], hn->Lmax, n, false)) return rc;
+    CU_CHECK(hn, cudaStreamWaitEvent(hn->s_main, ho->ev_comp[0], 0));
+    const float a0 = alpha0 + alpha_step * (float)done;
+#if defined(PC_EMULATE)
+    for (int c = 0; c < Cout; ++c)
+      for (size_t i = 0; i < n; ++i) {
+        const float al = std::fmin(1.0f, std::fmax(0.0f, a0 + alpha_step * (float)i));
+        float* d = hn->dout[0] + (size_t)c * hn->Lmax + i;
+        *d = (1.0f - al) * ho->dout[0][(size_t)c * ho->Lmax + i] + al * *d;
+      }
+#else
+    if (ho->Lmax != hn->Lmax) return fail(hn, B200CONV_EINVAL, "crossfade needs equal staging sizes (same head block and batch size)");
+    dim3 grid((unsigned)((n + 255) / 256), Cout, 1);
+    pc::k_xfade<<<grid, 256, 0, hn->s_main>>>(hn->dout[0], ho->dout[0], hn->dout[0], (long long)hn->Lmax, (long long)n, a0, alpha_step);
+    hn->launches++;
+    CU_CHECK(hn, cudaGetLastError());
+#endif
+    for (int c = 0; c < Cout; ++c)
+      CU_CHECK(hn, cudaMemcpyAsync(out[c] + done, hn->dout[0] + (size_t)c * hn->Lmax, n * sizeof(float), cudaMemcpyDeviceToHost, hn->s_main));
+    CU_CHECK(hn, cudaStreamSynchronize(hn->s_main));
+    done += n;
+  }
+  return B200CONV_OK;
 }
 
 int b200conv_clear(b200conv_t* h) {

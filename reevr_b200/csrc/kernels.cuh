@@ -933,6 +933,16 @@ __global__ void k_mix(MixParams P) {
   }
   P.out[(long long)o * P.out_stride + i] = acc;
 }
+
+// crossfade of two convolver outputs on the device (IR hot-swap, src/PluginProcessor.cpp:1800-1830):
+// dst[c][i] = (1 - a_i) * a[c][i] + a_i * b[c][i],  a_i = clamp(alpha0 + i*step, 0, 1); grid (ceil(n/256), C)
+__global__ void k_xfade(float* dst, const float* a, const float* b, long long stride, long long n, float alpha0, float step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long o = (long long)blockIdx.y * stride + i;
+  const float al = fminf(1.0f, fmaxf(0.0f, alpha0 + step * (float)i));
+  dst[o] = (1.0f - al) * a[o] + al * b[o];
+}
 #endif  // __CUDACC__
 
 

@@ -291,3 +291,34 @@ def test_device_mixdown_quad(lib):
     assert peak_err(yl, refs[0] + refs[3]) <= TOL and peak_err(yr, refs[1] + refs[2]) <= TOL
     e.set_routing(None, None)
     assert len(e.process([L[:64], R[:64], L[:64], R[:64]])) == 4
+
+
+def test_ir_hot_swap_prime_and_crossfade(lib):
+    """warm the incoming convolver with the last 0.25 s in ONE call (prime), then crossfade
+    old/new for 50 ms on the device — the sequence of src/PluginProcessor.cpp:1695-1750,1800-1830."""
+    sr, blk = 48000, 128
+    h_old = [orc.synth_ir(30000, c) for c in range(2)]
+    h_new = [orc.synth_ir(24000, c + 7) for c in range(2)]
+    n_hist, n_fade, n_after = sr // 4, 2400, 4000
+    x = [orc.synth_input(20000 + n_fade + n_after, c) for c in range(2)]
+    old = Engine(2, lib=lib)
+    new = Engine(2, lib=lib)
+    assert old.init_twostage(blk, 8192, h_old) and new.init_twostage(blk, 8192, h_new)
+    pre = [a[:20000] for a in x]
+    y_pre = old.process(pre)
+    new.prime([a[20000 - n_hist:20000] for a in x])                      # warm-up replay, no output
+    fade_in = [a[20000:20000 + n_fade] for a in x]
+    y_fade = old.process_xfade(new, fade_in, 0.0, 1.0 / n_fade)
+    y_post = new.process([a[20000 + n_fade:] for a in x])
+    for c in range(2):
+        oo, on = orc.OracleTwoStage(), orc.OracleTwoStage()
+        oo.init(blk, 8192, h_old[c])
+        on.init(blk, 8192, h_new[c])
+        r_pre = oo.process(pre[c])
+        on.process(x[c][20000 - n_hist:20000])
+        a = np.clip(np.arange(n_fade, dtype=np.float32) / n_fade, 0, 1)
+        r_fade = (1 - a) * oo.process(fade_in[c]) + a * on.process(fade_in[c])
+        r_post = on.process(x[c][20000 + n_fade:])
+        assert peak_err(y_pre[c], r_pre) <= TOL
+        assert peak_err(y_fade[c], r_fade) <= TOL
+        assert peak_err(y_post[c], r_post) <= TOL

@@ -91,6 +91,9 @@ struct b200conv {
   cudaEvent_t ev_join = nullptr;
   float* din[2] = {nullptr, nullptr};
   float* dout[2] = {nullptr, nullptr};
+  float* hpin_in = nullptr;       // pinned host staging of the latency path: all channels of a call in ONE copy
+  float* hpin_out = nullptr;
+  size_t hpin_cap = 0;            // samples per channel the staging holds
   unsigned long long launches = 0;
   // timing
   bool timing = false;
@@ -169,6 +172,9 @@ void free_all(b200conv* h) {
     cudaFree(h->din[i]); cudaFree(h->dout[i]); cudaFree(h->dch[i]);
     h->din[i] = h->dout[i] = h->dch[i] = nullptr;
   }
+  if (h->hpin_in) cudaFreeHost(h->hpin_in);
+  if (h->hpin_out) cudaFreeHost(h->hpin_out);
+  h->hpin_in = h->hpin_out = nullptr; h->hpin_cap = 0;
   h->ir_len.assign(h->C, 0);
   h->abs_pos = 0;
   h->Lmax = 0;
@@ -628,6 +634,10 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
     CU_CHECK(h, cudaMalloc(&h->dout[i], (size_t)C * h->Lmax * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&h->dch[i], (size_t)C * h->Lmax * sizeof(float)));
   }
+  // latency path staging (calls of up to max(64 head blocks, 16384) samples)
+  h->hpin_cap = std::min(h->Lmax, std::max((size_t)64 * B0, (size_t)16384));
+  CU_CHECK(h, cudaMallocHost((void**)&h->hpin_in, (size_t)C * h->hpin_cap * sizeof(float)));
+  CU_CHECK(h, cudaMallocHost((void**)&h->hpin_out, (size_t)C * h->hpin_cap * sizeof(float)));
   if (int rc = clear_state(h)) { free_all(h); return rc; }
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return B200CONV_OK;
@@ -1159,16 +1169,31 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
   const size_t B0 = h->stages[0].B;
   const size_t chunk = h->Lmax - B0;
   if (len <= chunk && len <= std::max((size_t)64 * B0, (size_t)16384)) {
-    // latency path: one stream, one group
-    for (int c = 0; c < Cin; ++c)
-      CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    // latency path: one stream, one group; all channels travel in ONE pinned H2D and ONE D2H copy
+    // (channel pitch = len), which matters for the 2-4 channel handles of a StereoConvolver
+    const bool packed = len <= h->hpin_cap;
+    const size_t pitch = packed ? len : h->Lmax;
+    if (packed) {
+      for (int c = 0; c < Cin; ++c) std::memcpy(h->hpin_in + (size_t)c * len, in[c], len * sizeof(float));
+      CU_CHECK(h, cudaMemcpyAsync(h->din[0], h->hpin_in, (size_t)Cin * len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    } else {
+      for (int c = 0; c < Cin; ++c)
+        CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    }
     const bool ov = h->cfg.shard_count > 1;
-    if (int rc = run_group(h, h->din[0], h->Lmax, h->dout[0], h->Lmax, len, ov)) return rc;
+    if (int rc = run_group(h, h->din[0], pitch, h->dout[0], pitch, len, ov)) return rc;
     if (ov) { if (int rc = join_post(h)) return rc; }
-    if (out)
-      for (int c = 0; c < Cout; ++c)
-        CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    if (out) {
+      if (packed) {
+        CU_CHECK(h, cudaMemcpyAsync(h->hpin_out, h->dout[0], (size_t)Cout * len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+      } else {
+        for (int c = 0; c < Cout; ++c)
+          CU_CHECK(h, cudaMemcpyAsync(out[c], h->dout[0] + (size_t)c * h->Lmax, len * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+      }
+    }
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    if (out && packed)
+      for (int c = 0; c < Cout; ++c) std::memcpy(out[c], h->hpin_out + (size_t)c * len, len * sizeof(float));
     return p2p_check(h);
   }
   // throughput path: H2D / compute / D2H of successive groups overlap on three streams

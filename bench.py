@@ -247,9 +247,9 @@ def main():
         C, block = wl["C"], wl["block"]
         L = wl["ir_s"] * wl["sr"]
         n = T * block
-        # single GPU: one launch group per step; sharded: 3 groups so that the NCCL reduce + inverse FFT of
+        # single GPU: one launch group per step; sharded: groups of 7104 blocks so that exchange + inverse FFT of
         # group i overlap the sweep of group i+1 (engine post stream)
-        groups = 1 if world == 1 else 3
+        groups = 1 if world == 1 else max(1, round(T / 7104))     # 7104 blocks = 8 full sweep waves
         gb = (T + groups - 1) // groups
         eng = Engine(C, device=local, max_batch_blocks=gb + 1, shard_rank=rank, shard_count=world, cmac_variant=args.variant)
         irs = [synth_ir(L, c) for c in range(C)]
@@ -387,7 +387,9 @@ def main():
         return res
 
     WL0 = wl
-    T = args.blocks or 7104
+    # one step = one batch of T blocks of the same stereo stream, identical at every N (strong scaling):
+    # 28416 blocks = 14.5 M frames = 5 min of audio; at N = 8 each GPU still sweeps ~0.5 ms per step
+    T = args.blocks or (28416 if args.workload == "metric" else 7104)
     main_res = run_workload(wl, T, args.steps, with_e2e=not args.no_e2e, with_clocks=True)
     extra = None
     if args.also_ir120 and args.workload == "metric":

@@ -621,7 +621,9 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
     st.push_back(x);
   }
   const int B0 = st[0].B;
-  int batch = h->cfg.max_batch_blocks > 0 ? h->cfg.max_batch_blocks : kDefaultBatch;
+  // default launch-group size: 4736 head blocks, but no more than ~4 M samples of staging per channel
+  int batch = h->cfg.max_batch_blocks > 0 ? h->cfg.max_batch_blocks
+                                          : std::max(64, std::min(kDefaultBatch, (int)((size_t)4194304 / (size_t)B0)));
   h->Lmax = (size_t)batch * B0;
   for (auto& x : st) h->Lmax = std::max(h->Lmax, (size_t)2 * x.B);
   h->stages = st;

@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="CMAC kernel variant (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stream", dest="no_stream", action="store_true", help="skip the streaming-kernel HBM roofline leg")
     ap.add_argument("--sweep", action="store_true", help="print a per-variant timing table to stderr")
     ap.add_argument("--mgpu", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange path (N > 1)")
     ap.add_argument("--also-ir120", dest="also_ir120", action="store_true",
@@ -397,6 +398,35 @@ def main():
         extra = {"value": r["value"], "unit": "M stereo frames/s", "ms_per_step": r["ms_per_step"], "config": r["config"],
                  "roofline_frac": r["roofline"]["frac"], "fp32_frac": r["roofline"]["fp32"]["frac"]}
 
+    # the memory-bound form of the sweep (real-time path, one block per launch) on a working set beyond L2:
+    # this is the kernel whose "% of HBM roofline" is a bandwidth statement
+    stream_roof = None
+    if world == 1 and not args.no_stream:
+        wl5 = WORKLOADS["ir120"]
+        C5, B5 = wl5["C"], wl5["block"]
+        e5 = Engine(C5, device=local)
+        assert e5.init_uniform(B5, [synth_ir(wl5["ir_s"] * wl5["sr"], c) for c in range(C5)])
+        P5 = int(e5.stages()[0]["partitions"])
+        xs5 = torch.from_numpy(np.stack([synth_input(B5 * 72, c) for c in range(C5)])).cuda()
+        y5 = torch.empty((C5, B5), device="cuda")
+        for i in range(8):
+            e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
+        e5.set_timing(True)
+        ts5 = []
+        for i in range(8, 72):
+            e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
+            ts5.append(e5.last_timing()["cmac_ms"])
+        e5.close()
+        t5 = statistics.median(ts5)
+        bytes5 = 16 * P5 * (B5 + 1) * C5                      # every H and FDL row read once per block step
+        peak, peak_kind = measured_peaks()
+        stream_roof = {"kernel": "k_cmac_stream_rows (one 512-sample block per launch)", "workload": wl5["desc"],
+                       "working_set_bytes": 2 * P5 * B5 * 8 * C5, "bound": "hbm", "launch_ms": t5,
+                       "achieved": bytes5 / (t5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": bytes5 / (t5 * 1e-3) / 1e9 / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                       "algorithmic_bytes_per_launch": bytes5, "traffic": 188137728,
+                       "traffic_source": "profiles/r01_prof_final_stream_cfg5.txt (ncu: 184.35 MB read + 3.79 MB written)"}
+
     if args.sweep and rank == 0 and world == 1:
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--blocks", str(T)], stdout=sys.stderr)
 
@@ -417,6 +447,8 @@ def main():
         }
         if extra:
             line["ir120"] = extra
+        if stream_roof:
+            line["roofline_stream"] = stream_roof
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

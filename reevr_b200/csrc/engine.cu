@@ -241,16 +241,23 @@ void launch_fwd_l(const pc::FwdParams& P, const FftGeom& g, cudaStream_t st) {
 }
 template <int L>
 void launch_inv_l(const pc::InvParams& P, const FftGeom& g, cudaStream_t st) {
-  if (g.tws) pc::k_inv_fft_ola<(1 << L), true><<<g.grid, g.block, g.smem, st>>>(P);
-  else pc::k_inv_fft_ola<(1 << L), false><<<g.grid, g.block, g.smem, st>>>(P);
+  if (P.n_partials > 1) {
+    if (g.tws) pc::k_inv_fft_ola<(1 << L), true, true><<<g.grid, g.block, g.smem, st>>>(P);
+    else pc::k_inv_fft_ola<(1 << L), false, true><<<g.grid, g.block, g.smem, st>>>(P);
+  } else {
+    if (g.tws) pc::k_inv_fft_ola<(1 << L), true, false><<<g.grid, g.block, g.smem, st>>>(P);
+    else pc::k_inv_fft_ola<(1 << L), false, false><<<g.grid, g.block, g.smem, st>>>(P);
+  }
 }
 template <int L>
 bool fft_set_smem_attr() {
   const int kSmem = 200 * 1024;   // B = 4096: 48 KB table + 64 KB ping-pong buffers; B = 8192: 128 KB buffers
   bool ok = cudaFuncSetAttribute(pc::k_fwd_fft<(1 << L), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(pc::k_fwd_fft<(1 << L), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
   return ok;
 }
 #define PC_FOR_EACH_LOG2(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)

@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(32 * TW) k_cmac_batch(CmacParams P) {
 
 
 // same geometry as k_fwd_fft
-template <int M, bool TWS>
+template <int M, bool TWS, bool PART>
 __global__ void __launch_bounds__(512) k_inv_fft_ola(InvParams P) {
   extern __shared__ float2 pc_smem[];
   constexpr bool WARP = fft_warp_mode(M);
@@ -783,8 +783,9 @@ __global__ void __launch_bounds__(512) k_inv_fft_ola(InvParams P) {
     o.abs0 = P.abs0 + (long long)blk * M;
     const float2* Yt = P.Y + (long long)c * P.y_cstride + (P.yrow0 + blk) * P.y_rstride;
     const float2* Yp = Yt - P.y_rstride;
+    const int np = PART ? P.n_partials : 1;      // PART = false: single-GPU path without the partial-slot sums
 #pragma unroll 4
-    for (int k = tx; k <= M / 2; k += NT) inv_pre(Yt, Yp, bufA, tw, M, k, P.n_partials, P.partial_stride);
+    for (int k = tx; k <= M / 2; k += NT) inv_pre(Yt, Yp, bufA, tw, M, k, np, P.partial_stride);
   }
   fft_sync<WARP>();
   if constexpr (M == 1) {

@@ -12,11 +12,15 @@
 //   X   [C][R][B]       input-spectrum timeline = the frequency-domain delay line, linear:
 //                       row `head` is the open block; partition p of output block t reads row
 //                       head + t - p.  Compacted (history moved to the front) when full.
-//   Y   [1+T][C][B]     spectra of the current batch; row 0 = last completed block of the
-//                       previous batch (the overlap state, FFTConvolver.cpp:204 kept in the
-//                       frequency domain)
+//   Y[2] [1+T][C][B]    spectra of the current launch group (double-buffered by group so that reduce +
+//                       inverse FFT of group i overlap the sweep of group i+1); row 0 = last completed
+//                       block of the previous group (the overlap state, FFTConvolver.cpp:204 kept in
+//                       the frequency domain)
 //   inbuf [C][B + Lmax] time-domain input of the open block + this call's samples
 //   fut [C][ring]       (stages >= 1) look-ahead output ring, indexed by absolute position
+// Streams: s_main (forward FFT + sweep), s_post (exchange/reduce + inverse FFT + mixdown), s_in / s_out
+// (PCIe copies of the pipelined host path).  Multi-GPU: partition-range shards with either a reduce hook
+// (NCCL) or the fused slot exchange over peer memory (run_group_p2p).
 #if defined(PC_EMULATE)
 #include "cuda_emu.h"      // tests/emu: host stand-in for the CUDA runtime (test infrastructure)
 #else
@@ -110,7 +114,7 @@ struct b200conv {
   int n_in = 0, n_out = 0;
   int in_map[8] = {};
   float mix[64] = {};
-  float* dch[2] = {nullptr, nullptr};       // per-convolver outputs [C][Lmax] before the mixdown
+  float* dch[1] = {nullptr};                // per-convolver outputs [C][Lmax] before the mixdown
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -169,9 +173,10 @@ void free_all(b200conv* h) {
   for (auto& s : h->stages) free_stage(s);
   h->stages.clear();
   for (int i = 0; i < 2; ++i) {
-    cudaFree(h->din[i]); cudaFree(h->dout[i]); cudaFree(h->dch[i]);
-    h->din[i] = h->dout[i] = h->dch[i] = nullptr;
+    cudaFree(h->din[i]); cudaFree(h->dout[i]);
+    h->din[i] = h->dout[i] = nullptr;
   }
+  cudaFree(h->dch[0]); h->dch[0] = nullptr;
   if (h->hpin_in) cudaFreeHost(h->hpin_in);
   if (h->hpin_out) cudaFreeHost(h->hpin_out);
   h->hpin_in = h->hpin_out = nullptr; h->hpin_cap = 0;
@@ -641,8 +646,8 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
   for (int i = 0; i < 2; ++i) {
     CU_CHECK(h, cudaMalloc(&h->din[i], (size_t)C * h->Lmax * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&h->dout[i], (size_t)C * h->Lmax * sizeof(float)));
-    CU_CHECK(h, cudaMalloc(&h->dch[i], (size_t)C * h->Lmax * sizeof(float)));
   }
+  CU_CHECK(h, cudaMalloc(&h->dch[0], (size_t)C * h->Lmax * sizeof(float)));
   // latency path staging (calls of up to max(64 head blocks, 16384) samples)
   h->hpin_cap = std::min(h->Lmax, std::max((size_t)64 * B0, (size_t)16384));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_in, (size_t)C * h->hpin_cap * sizeof(float)));

@@ -232,6 +232,23 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fall-back)")
     torch.cuda.set_device(local)
+    # Pinned staging buffers must live on the NUMA node the GPU hangs off, otherwise every H2D / D2H of the
+    # e2e path crosses the socket interconnect (and with sharding the slowest rank's link paces all of them):
+    # run this process on the GPU's CPU-affinity set while the buffers are allocated and first touched.
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = "not bound"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (max(all_cpus) // 64) + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & all_cpus
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa_note = f"process bound to the GPU's {len(cpus)} local CPUs for pinned allocations"
+    except Exception as ex:       # best effort
+        numa_note = f"not bound ({type(ex).__name__})"
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
@@ -364,7 +381,8 @@ def main():
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e = {"value": n * steps / float(dt.item()) / 1e6, "unit": "M stereo frames/s",
                    "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4 if rank == 0 else 0,
-                   "how": "b200conv_process() on pinned host buffers, wall clock, H2D / compute / D2H pipelined on separate streams"}
+                   "how": "b200conv_process() on pinned host buffers, wall clock, H2D / compute / D2H pipelined on separate streams",
+                   "numa": numa_note}
         res = {
             "value": value, "ms_per_step": ms_per_step, "launches": int(launches), "clocks": clocks, "e2e": e2e,
             "config": {"workload": wl["desc"], "channels": C, "ir_taps": eng.ir_len(0), "block": block, "partitions": P,
@@ -432,6 +450,7 @@ def main():
 
     if rank == 0:
         cpu = None
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core again
         if not args.no_cpu and world == 1:
             cpu = cpu_reference_run(wl, seconds_target=12.0, threads=os.cpu_count() or 1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "parallel_ms_per_block")}

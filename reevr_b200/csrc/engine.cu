@@ -746,6 +746,7 @@ int p2p_alloc(b200conv* h) {
   {
     cudaFuncAttributes fa;
     CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_p2p_barrier));
+    CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_copy_rows));
 #define PC_PRELOAD(BS) \
     CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_cmac_batch2<16, 4, 4, BS, 3>)); \
     CU_CHECK(h, cudaFuncGetAttributes(&fa, pc::k_cmac_batch2<8, 4, 4, BS, 4>));
@@ -805,6 +806,21 @@ int p2p_barrier(b200conv* h, cudaStream_t st) {
   return 0;
 }
 
+// device-to-device row copy as a kernel (never a copy-engine copy: see k_copy_rows)
+int copy_rows_kernel(b200conv* h, float* dst, size_t dpitch, const float* src, size_t spitch, size_t width, int rows, cudaStream_t st) {
+  if (width == 0 || rows == 0) return 0;
+#if defined(PC_EMULATE)
+  (void)st;
+  for (int r = 0; r < rows; ++r) std::memmove(dst + (size_t)r * dpitch, src + (size_t)r * spitch, width * sizeof(float));
+#else
+  dim3 grid((unsigned)((width + 255) / 256), rows, 1);
+  pc::k_copy_rows<<<grid, 256, 0, st>>>(dst, (long long)dpitch, src, (long long)spitch, (long long)width, rows);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+#endif
+  return 0;
+}
+
 // one launch group of a single-stage sharded handle through the slot exchange
 int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n) {
   const int C = h->C, G = h->cfg.shard_count, g = h->cfg.shard_rank;
@@ -852,9 +868,10 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
 
   const int j0 = std::min(nb, g * per), j1 = std::min(nb, (g + 1) * per);
   if (j1 > j0) {
-    if (g == 0)   // halo of the first slice = last completed row of the previous group (all G partials)
-      CU_CHECK(h, cudaMemcpy2DAsync(h->Yx[yb], h->xslot * sizeof(float2), h->Hh + (size_t)h->hidx * G * row,
-                                    row * sizeof(float2), row * sizeof(float2), G, cudaMemcpyDeviceToDevice, ps));
+    if (g == 0) { // halo of the first slice = last completed row of the previous group (all G partials)
+      if (int rc = copy_rows_kernel(h, reinterpret_cast<float*>(h->Yx[yb]), h->xslot * 2,
+                                    reinterpret_cast<const float*>(h->Hh + (size_t)h->hidx * G * row), row * 2, row * 2, G, ps)) return rc;
+    }
     pc::InvParams ip{};
     ip.Y = h->Yx[yb]; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
     ip.tw = s.tw; ip.M = B; ip.nblocks = j1 - j0; ip.scale = 1.0f / (float)B;
@@ -865,9 +882,9 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
     if (int rc = launch_inv(h, ip, C, ps)) return rc;
   }
   if (int rc = p2p_barrier(h, ps)) return rc;          // every slice of the audio is in shard 0's exchange buffer
-  if (g == 0 && out_dev)
-    CU_CHECK(h, cudaMemcpy2DAsync(out_dev, out_stride * sizeof(float), h->xout[yb], h->Lmax * sizeof(float),
-                                  n * sizeof(float), C, cudaMemcpyDeviceToDevice, ps));
+  if (g == 0 && out_dev) {
+    if (int rc = copy_rows_kernel(h, out_dev, out_stride, h->xout[yb], h->Lmax, n, C, ps)) return rc;
+  }
   CU_CHECK(h, cudaEventRecord(s.ev_post[yb], ps));
 
   if (complete > 0) {

@@ -944,6 +944,14 @@ __global__ void k_xfade(float* dst, const float* a, const float* b, long long st
   const float al = fminf(1.0f, fmaxf(0.0f, alpha0 + step * (float)i));
   dst[o] = (1.0f - al) * a[o] + al * b[o];
 }
+
+// strided row copy on the SMs (rows x width floats); used where a copy-engine copy queued behind a spinning
+// flag barrier would block the H2D copies of the following launch groups (slot-exchange path)
+__global__ void k_copy_rows(float* dst, long long dpitch, const float* src, long long spitch, long long width, int rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i < width && r < rows) dst[(long long)r * dpitch + i] = src[(long long)r * spitch + i];
+}
 #endif  // __CUDACC__
 
 

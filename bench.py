@@ -118,7 +118,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference timing (oracle/_ref = the unmodified reference sources; falls back to the C port)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, seconds_target: float, threads: int):
+def cpu_reference_run(wl, seconds_target: float, threads: int, single_thread_leg: bool = False):
     """Runs `threads` independent stereo (C-channel) instances of the reference's uniform
     FFTConvolver in parallel, each over the same bounded sample; returns dict for cpu_baseline."""
     from oracle import oracle as orc
@@ -155,8 +155,20 @@ def cpu_reference_run(wl, seconds_target: float, threads: int):
             th.join()
         return max(done) - t0
 
+    # "as the plugin does it" (src/dsp/StereoConvolver.cpp:35-36): ONE thread, the C channels serially
+    single = None
+    if single_thread_leg:
+        xs1 = [orc.synth_input(64 * block, c) for c in range(C)]
+        t1 = time.perf_counter()
+        for c in range(C):
+            insts[0][c].run(xs1[c], block)
+        single = 64 * block / (time.perf_counter() - t1) / 1e6
+        for c in range(C):
+            insts[0][c].clear()
+
     # calibrate with ALL threads running (the sweep is memory-bound: per-thread speed drops with the
     # thread count), then size the sample for ~seconds_target of wall time
+    run_all(16)                      # warm-up: first touch of every instance's FDL / spectra
     cal = 8
     per_block = run_all(cal) / cal
     nblk = int(max(16, min(16384, seconds_target / max(per_block, 1e-9))))
@@ -168,6 +180,7 @@ def cpu_reference_run(wl, seconds_target: float, threads: int):
         "sample": f"{threads} independent {C}-channel instances x {nblk} blocks of {block} (ctypes, GIL released), "
                   f"uniform FFTConvolver, {wl['desc']}",
         "seconds": dt, "parallel_ms_per_block": per_block * 1e3,
+        "single_thread_value": single,
     }
 
 
@@ -452,8 +465,8 @@ def main():
         cpu = None
         os.sched_setaffinity(0, all_cpus)          # the CPU baseline uses every host core again
         if not args.no_cpu and world == 1:
-            cpu = cpu_reference_run(wl, seconds_target=12.0, threads=os.cpu_count() or 1)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "parallel_ms_per_block")}
+            cpu = cpu_reference_run(wl, seconds_target=12.0, threads=os.cpu_count() or 1, single_thread_leg=True)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "parallel_ms_per_block", "single_thread_value")}
         C = wl["C"]
         line = {
             "metric": "stereo partitioned-convolution throughput (IR 10 s @ 48 kHz, block 512)" if args.workload == "metric"

@@ -133,6 +133,7 @@ def cpu_reference_run(wl, seconds_target: float, threads: int, single_thread_leg
         for c in range(C):
             k = cls()
             k.init(block, irs[c])
+            k.clear()                # zero-fills (= first-touches) the whole frequency-domain delay line
             convs.append(k)
         return convs
 

@@ -105,7 +105,8 @@ void*  b200conv_stream(const b200conv_t* h);                  /* cudaStream_t of
 /* Multi-GPU partition-range sharding: with shard_count > 1 every handle computes
  * the partial spectrum sum over its own partition range; between the CMAC sweep and the
  * inverse FFT the engine calls `reduce(user, dev_ptr, n_floats, stream)` which must sum the
- * buffer over all shards into shard 0 (ncclReduce on that stream).  Only shard 0 produces output. */
+ * buffer over all shards into shard 0 (ncclReduce on that stream).  Only shard 0 produces output;
+ * the other shards do not write their `out` buffers. */
 typedef int (*b200conv_reduce_fn)(void* user, float* dev_buf, size_t n_floats, void* cuda_stream);
 int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
 

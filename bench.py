@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--no-stream", dest="no_stream", action="store_true", help="skip the streaming-kernel HBM roofline leg")
     ap.add_argument("--sweep", action="store_true", help="print a per-variant timing table to stderr")
     ap.add_argument("--mgpu", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange path (N > 1)")
+    ap.add_argument("--e2e-bcast", dest="e2e_bcast", action="store_true",
+                    help="N > 1, p2p: rank 0 uploads the input and broadcasts it over NVLink (off by default: not yet timed)")
     ap.add_argument("--also-ir120", dest="also_ir120", action="store_true",
                     help="additionally time config 5 (120 s IR) and attach it as `ir120`")
     args = ap.parse_args()
@@ -299,6 +301,8 @@ def main():
             if args.mgpu == "p2p":
                 try:
                     attach_p2p(eng)                   # fused slot exchange over NVLink peer memory
+                    if args.e2e_bcast:                # host-pointer path: only rank 0 crosses PCIe
+                        eng.p2p_set_input_broadcast(True)
                     mgpu_path = ("partition-range shards + fused slot exchange: sweep epilogue stores partial rows into "
                                  "the owner GPU's slot over NVLink, flag barrier, per-slice inverse FFT (no NCCL on the data path)")
                 except Exception as ex:               # both are GPU paths; say which one ran

@@ -141,6 +141,11 @@ int b200conv_process_xfade(b200conv_t* h_old, b200conv_t* h_new, const float* co
 size_t b200conv_p2p_blob_size(const b200conv_t* h);
 int    b200conv_p2p_export(b200conv_t* h, void* blob, int mode);
 int    b200conv_p2p_import(b200conv_t* h, const void* all_blobs /* shard_count * blob_size bytes */);
+/* Host-pointer calls (b200conv_process) on a slot-exchange handle: with the input broadcast enabled only
+ * shard 0 reads its `in` buffers and crosses PCIe; it stores every launch group into the peers' staging
+ * buffers over NVLink (the other shards' `in` arguments are ignored).  Off by default (round 1: implemented and
+ * covered by the in-process tests, not yet timed on a multi-GPU box). */
+int    b200conv_p2p_set_input_broadcast(b200conv_t* h, int enable);
 /* Host-side barrier used instead of the flag kernel by the CPU emulation build (tests only). */
 typedef int (*b200conv_barrier_fn)(void* user);
 int    b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* user);

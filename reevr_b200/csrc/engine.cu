@@ -130,6 +130,11 @@ struct b200conv {
   float2* peerHh0 = nullptr;
   float* peer_xout0[2] = {nullptr, nullptr};
   unsigned int* peer_flags[8] = {};
+  bool bcast_in = false;                    // shard 0 uploads the input and stores it into the peers' staging (NVLink)
+  float* peer_din[8][2] = {};               // every shard's din[0..1] (mapped on shard 0)
+  unsigned int in_epoch = 0;                // epoch of the "input landed" barrier (flag words 16..23)
+  unsigned long long xgrp = 0;              // slot-exchange groups issued so far
+  cudaEvent_t ev_b1[2] = {nullptr, nullptr};   // first barrier of group (xgrp & 1) passed: peers finished reading din
   std::vector<void*> ipc_opened;
   b200conv_barrier_fn host_barrier = nullptr;
   void* host_barrier_user = nullptr;
@@ -165,7 +170,8 @@ void p2p_release(b200conv* h) {
   h->ipc_opened.clear();
   cudaFree(h->Yx[0]); cudaFree(h->Yx[1]); cudaFree(h->Hh); cudaFree(h->xout[0]); cudaFree(h->xout[1]); cudaFree(h->xflags);
   h->Yx[0] = h->Yx[1] = nullptr; h->Hh = nullptr; h->xout[0] = h->xout[1] = nullptr; h->xflags = nullptr;
-  h->p2p_on = false; h->hidx = 0; h->bar_epoch = 0;
+  h->p2p_on = false; h->hidx = 0; h->bar_epoch = 0; h->in_epoch = 0; h->xgrp = 0; h->bcast_in = false;
+  for (int i = 0; i < 2; ++i) { if (h->ev_b1[i]) cudaEventDestroy(h->ev_b1[i]); h->ev_b1[i] = nullptr; }
 }
 
 void free_all(b200conv* h) {
@@ -722,7 +728,7 @@ int compact_timeline(b200conv* h, Stage& s) {
 
 // ---- slot exchange (fused multi-GPU path) ------------------------------------------------------
 struct P2PRecord { unsigned long long kind; unsigned long long ptr; unsigned char ipc[64]; };
-constexpr int kP2PBuffers = 6;    // Yx[0], Yx[1], Hh, xout[0], xout[1], flags
+constexpr int kP2PBuffers = 8;    // Yx[0], Yx[1], Hh, xout[0], xout[1], flags, din[0], din[1]
 
 int p2p_alloc(b200conv* h) {
   if (h->Yx[0]) return 0;
@@ -738,8 +744,10 @@ int p2p_alloc(b200conv* h) {
   }
   CU_CHECK(h, cudaMalloc(&h->Hh, (size_t)3 * G * row * sizeof(float2)));
   CU_CHECK(h, cudaMemsetAsync(h->Hh, 0, (size_t)3 * G * row * sizeof(float2), h->s_main));
-  CU_CHECK(h, cudaMalloc(&h->xflags, 16 * sizeof(unsigned int)));
-  CU_CHECK(h, cudaMemsetAsync(h->xflags, 0, 16 * sizeof(unsigned int), h->s_main));
+  CU_CHECK(h, cudaMalloc(&h->xflags, 32 * sizeof(unsigned int)));
+  CU_CHECK(h, cudaMemsetAsync(h->xflags, 0, 32 * sizeof(unsigned int), h->s_main));
+  for (int i = 0; i < 2; ++i)
+    if (!h->ev_b1[i]) CU_CHECK(h, cudaEventCreateWithFlags(&h->ev_b1[i], cudaEventDisableTiming));
 #if !defined(PC_EMULATE)
   // Load every kernel / driver copy routine the exchange flow launches NOW: a lazy module load
   // synchronises the context and must not happen while a peer's flag barrier is spinning on this device.
@@ -780,8 +788,10 @@ int p2p_check(b200conv* h) {
   return 0;
 }
 
-int p2p_barrier(b200conv* h, cudaStream_t st) {
-  h->bar_epoch++;
+// bank 0: exchange barriers (flag words 0..7, issued on s_post); bank 1: "input landed" barriers (words 16..23)
+int p2p_barrier(b200conv* h, cudaStream_t st, int bank = 0) {
+  unsigned int& epoch = bank == 0 ? h->bar_epoch : h->in_epoch;
+  epoch++;
 #if defined(PC_EMULATE)
   (void)st;
   if (!h->host_barrier) return fail(h, B200CONV_ESTATE, "emulated slot exchange needs a host barrier");
@@ -795,10 +805,10 @@ int p2p_barrier(b200conv* h, cudaStream_t st) {
     return 0;
   }
   pc::BarrierParams bp{};
-  for (int g = 0; g < h->cfg.shard_count; ++g) bp.peer_flags[g] = h->peer_flags[g];
-  bp.my_flags = h->xflags;
+  for (int g = 0; g < h->cfg.shard_count; ++g) bp.peer_flags[g] = h->peer_flags[g] + 16 * bank;
+  bp.my_flags = h->xflags + 16 * bank;
   bp.error_word = h->xflags + 8;
-  bp.rank = h->cfg.shard_rank; bp.G = h->cfg.shard_count; bp.epoch = h->bar_epoch;
+  bp.rank = h->cfg.shard_rank; bp.G = h->cfg.shard_count; bp.epoch = epoch;
   pc::k_p2p_barrier<<<1, 32, 0, st>>>(bp);
   h->launches++;
   CU_CHECK(h, cudaGetLastError());
@@ -865,6 +875,8 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
   CU_CHECK(h, cudaStreamWaitEvent(ps, s.ev_sweep[yb], 0));
 
   if (int rc = p2p_barrier(h, ps)) return rc;          // every GPU's partial rows have landed
+  CU_CHECK(h, cudaEventRecord(h->ev_b1[h->xgrp & 1], ps));   // ... hence every GPU is done reading this group's input
+  h->xgrp++;
 
   const int j0 = std::min(nb, g * per), j1 = std::min(nb, (g + 1) * per);
   if (j1 > j0) {
@@ -1186,6 +1198,32 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
   return B200CONV_OK;
 }
 
+// Host -> device staging of one launch group (n samples per channel from in[c] + off into din[b], channel pitch
+// `pitch`) on stream st.  With the slot exchange's input broadcast only shard 0 touches PCIe: it uploads the
+// group, stores it into every peer's din[b] over NVLink and an "input landed" flag barrier releases the peers.
+static int stage_input(b200conv_t* h, int b, const float* const* in, size_t off, size_t n, size_t pitch, int Cin,
+                       const float* packed_src, cudaStream_t st) {
+  const bool bc = h->p2p_on && h->bcast_in;
+  if (!bc || h->cfg.shard_rank == 0) {
+    if (packed_src) {
+      CU_CHECK(h, cudaMemcpyAsync(h->din[b], packed_src, (size_t)Cin * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+      for (int c = 0; c < Cin; ++c)
+        CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * pitch, in[c] + off, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (bc) {
+    if (h->cfg.shard_rank == 0) {
+      // the peers read din[b] in the forward FFT of the group two exchange groups ago: its first barrier has passed
+      CU_CHECK(h, cudaStreamWaitEvent(st, h->ev_b1[h->xgrp & 1], 0));
+      for (int r = 1; r < h->cfg.shard_count; ++r)
+        if (int rc = copy_rows_kernel(h, h->peer_din[r][b], pitch, h->din[b], pitch, n, Cin, st)) return rc;
+    }
+    if (int rc = p2p_barrier(h, st, 1)) return rc;
+  }
+  return 0;
+}
+
 static int process_impl(b200conv_t* h, const float* const* in, float* const* out_user, size_t len) {
   REQUIRE_CUDA(h);
   if (len == 0) return B200CONV_OK;
@@ -1207,13 +1245,10 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
     // (channel pitch = len), which matters for the 2-4 channel handles of a StereoConvolver
     const bool packed = len <= h->hpin_cap;
     const size_t pitch = packed ? len : h->Lmax;
-    if (packed) {
+    const bool uploads = !(h->p2p_on && h->bcast_in) || h->cfg.shard_rank == 0;
+    if (packed && uploads)
       for (int c = 0; c < Cin; ++c) std::memcpy(h->hpin_in + (size_t)c * len, in[c], len * sizeof(float));
-      CU_CHECK(h, cudaMemcpyAsync(h->din[0], h->hpin_in, (size_t)Cin * len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
-    } else {
-      for (int c = 0; c < Cin; ++c)
-        CU_CHECK(h, cudaMemcpyAsync(h->din[0] + (size_t)c * h->Lmax, in[c], len * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
-    }
+    if (int rc = stage_input(h, 0, in, 0, len, pitch, Cin, packed ? h->hpin_in : nullptr, h->s_main)) return rc;
     const bool ov = h->cfg.shard_count > 1;
     if (int rc = run_group(h, h->din[0], pitch, h->dout[0], pitch, len, ov)) return rc;
     if (ov) { if (int rc = join_post(h)) return rc; }
@@ -1247,8 +1282,7 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
     const int b = i & 1;
     const size_t n = std::min(len - done, grp);
     if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_din[b], 0));     // din[b] free again
-    for (int c = 0; c < Cin; ++c)
-      CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * h->Lmax, in[c] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+    if (int rc = stage_input(h, b, in, done, n, h->Lmax, Cin, nullptr, h->s_in)) return rc;
     CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
     CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_h2d[b], 0));
     if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_post, h->ev_d2h[b], 0));    // dout[b] drained
@@ -1417,7 +1451,7 @@ int b200conv_p2p_export(b200conv_t* h, void* blob, int mode) {
   if (int rc = set_device(h)) return rc;
   if (int rc = p2p_alloc(h)) return rc;
   h->p2p_mode = mode;
-  void* bufs[kP2PBuffers] = {h->Yx[0], h->Yx[1], h->Hh, h->xout[0], h->xout[1], h->xflags};
+  void* bufs[kP2PBuffers] = {h->Yx[0], h->Yx[1], h->Hh, h->xout[0], h->xout[1], h->xflags, h->din[0], h->din[1]};
   P2PRecord* rec = static_cast<P2PRecord*>(blob);
   for (int i = 0; i < kP2PBuffers; ++i) {
     std::memset(&rec[i], 0, sizeof(P2PRecord));
@@ -1456,7 +1490,7 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
         return fail(h, B200CONV_EINVAL, "IPC records in the emulation build");
 #else
         // only the buffers this shard touches are mapped: every peer's Yx + flags, shard 0's Hh + xout
-        const bool needed = (i <= 1) || (i == 5) || (r == 0);
+        const bool needed = (i <= 1) || (i == 5) || (r == 0 && i <= 4) || (me == 0 && i >= 6);
         ptrs[i] = nullptr;
         if (needed) {
           cudaIpcMemHandle_t hd;
@@ -1472,6 +1506,8 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
     h->peerYx[r][0] = static_cast<float2*>(ptrs[0]);
     h->peerYx[r][1] = static_cast<float2*>(ptrs[1]);
     h->peer_flags[r] = static_cast<unsigned int*>(ptrs[5]);
+    h->peer_din[r][0] = static_cast<float*>(ptrs[6]);
+    h->peer_din[r][1] = static_cast<float*>(ptrs[7]);
     if (r == 0) {
       h->peerHh0 = static_cast<float2*>(ptrs[2]);
       h->peer_xout0[0] = static_cast<float*>(ptrs[3]);
@@ -1479,6 +1515,13 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
     }
   }
   h->p2p_on = true;
+  return B200CONV_OK;
+}
+
+int b200conv_p2p_set_input_broadcast(b200conv_t* h, int enable) {
+  if (!h) return B200CONV_EINVAL;
+  if (enable && !h->p2p_on) return fail(h, B200CONV_ESTATE, "input broadcast needs an attached slot exchange");
+  h->bcast_in = enable != 0;
   return B200CONV_OK;
 }
 

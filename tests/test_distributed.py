@@ -123,7 +123,7 @@ def test_sequential_fake_of_the_reduce(backend, G):
     assert np.max(np.abs(outs - yo)) / np.max(np.abs(yo)) <= TOL
 
 
-def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_blocks=0):
+def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_blocks=0, bcast=False):
     """G shards of one convolver in G threads of this process (raw-pointer slot exchange)."""
     import threading
     lib_ = get_lib(lib_name)
@@ -146,9 +146,13 @@ def _p2p_threads(lib_name, G, uniform_block, ir, x, chunks, C=1, max_batch_block
             # several spinning flag kernels would block each other through the shared hardware queues) —
             # the flag kernel itself is exercised by the multi-process multi-GPU runs of bench.py
             e.p2p_attach(allgather, mode=1, host_barrier=lambda: (host_bar.wait(120), 0)[1])
+            if bcast:
+                e.p2p_set_input_broadcast(True)
             ys, pos = [], 0
             for k in chunks:
-                ys.append(e.process([x[pos:pos + k]] * C)[0])
+                # with the input broadcast only shard 0's input matters: feed the others garbage
+                src = x[pos:pos + k] if (rank == 0 or not bcast) else np.full(k, 1e3, np.float32)
+                ys.append(e.process([src] * C)[0])
                 pos += k
             outs[rank] = np.concatenate(ys)
             gather_bar.wait(120)      # nobody frees exchange buffers while a peer may still touch them
@@ -180,4 +184,19 @@ def test_slot_exchange_in_process(backend, G):
     yo = o.process(x)
     for chunks in ([n], [5000, 128 * 40, 3, n - 5000 - 128 * 40 - 3], [128 * 50] * 3 + [77]):
         y = _p2p_threads(backend, G, 128, h, x, chunks, max_batch_blocks=64)
+        assert np.max(np.abs(y - yo)) / np.max(np.abs(yo)) <= TOL, chunks
+
+
+@pytest.mark.parametrize("backend,G", [("emu", 2), ("emu", 4), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
+def test_slot_exchange_input_broadcast(backend, G):
+    """Host-pointer calls with the input broadcast: only shard 0 uploads, the peers get every launch group
+    through their staging buffers (they are fed garbage here) — short latency-path calls and long pipelined ones."""
+    h = orc.synth_ir(6000)
+    n = 128 * 200 + 50
+    x = orc.synth_input(n)
+    o = orc.OracleUniform()
+    o.init(128, h)
+    yo = o.process(x)
+    for chunks in ([128 * 130, 700, 128, 128, n - 128 * 132 - 700], [n]):
+        y = _p2p_threads(backend, G, 128, h, x, chunks, max_batch_blocks=48, bcast=True)
         assert np.max(np.abs(y - yo)) / np.max(np.abs(yo)) <= TOL, chunks

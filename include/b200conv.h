@@ -141,6 +141,8 @@ int b200conv_process_xfade(b200conv_t* h_old, b200conv_t* h_new, const float* co
 size_t b200conv_p2p_blob_size(const b200conv_t* h);
 int    b200conv_p2p_export(b200conv_t* h, void* blob, int mode);
 int    b200conv_p2p_import(b200conv_t* h, const void* all_blobs /* shard_count * blob_size bytes */);
+/* Back to the reduce-hook path (e.g. when the import failed on some other shard: all shards must agree). */
+int    b200conv_p2p_detach(b200conv_t* h);
 /* Host-pointer calls (b200conv_process) on a slot-exchange handle: with the input broadcast enabled only
  * shard 0 reads its `in` buffers and crosses PCIe; it stores every launch group into the peers' staging
  * buffers over NVLink (the other shards' `in` arguments are ignored).  Off by default (round 1: implemented and

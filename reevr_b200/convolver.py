@@ -197,6 +197,10 @@ class Engine:
         joined = C.create_string_buffer(b"".join(blobs), n * len(blobs))
         self._check(self._l.b200conv_p2p_import(self._h, joined), "p2p_import")
 
+    def p2p_detach(self):
+        """Leave the slot-exchange path (every shard must do the same); the reduce hook takes over again."""
+        self._check(self._l.b200conv_p2p_detach(self._h), "p2p_detach")
+
     def p2p_set_input_broadcast(self, on: bool = True):
         """Host-pointer calls: only shard 0 uploads the input; the peers receive it over NVLink."""
         self._check(self._l.b200conv_p2p_set_input_broadcast(self._h, int(on)), "p2p_set_input_broadcast")

@@ -131,7 +131,8 @@ struct b200conv {
   float* peer_xout0[2] = {nullptr, nullptr};
   unsigned int* peer_flags[8] = {};
   bool bcast_in = false;                    // shard 0 uploads the input and stores it into the peers' staging (NVLink)
-  float* peer_din[8][2] = {};               // every shard's din[0..1] (mapped on shard 0)
+  float* peer_din[8][2] = {};               // every shard's din[0..1] (mapped on shard 0 when the broadcast is enabled)
+  std::vector<unsigned char> din_records;   // the peers' exported din records, opened lazily
   unsigned int in_epoch = 0;                // epoch of the "input landed" barrier (flag words 16..23)
   unsigned long long xgrp = 0;              // slot-exchange groups issued so far
   cudaEvent_t ev_b1[2] = {nullptr, nullptr};   // first barrier of group (xgrp & 1) passed: peers finished reading din
@@ -1490,7 +1491,8 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
         return fail(h, B200CONV_EINVAL, "IPC records in the emulation build");
 #else
         // only the buffers this shard touches are mapped: every peer's Yx + flags, shard 0's Hh + xout
-        const bool needed = (i <= 1) || (i == 5) || (r == 0 && i <= 4) || (me == 0 && i >= 6);
+        // (the din records, i >= 6, are only opened if the input broadcast gets enabled)
+        const bool needed = (i <= 1) || (i == 5) || (r == 0 && i <= 4);
         ptrs[i] = nullptr;
         if (needed) {
           cudaIpcMemHandle_t hd;
@@ -1506,14 +1508,16 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
     h->peerYx[r][0] = static_cast<float2*>(ptrs[0]);
     h->peerYx[r][1] = static_cast<float2*>(ptrs[1]);
     h->peer_flags[r] = static_cast<unsigned int*>(ptrs[5]);
-    h->peer_din[r][0] = static_cast<float*>(ptrs[6]);
-    h->peer_din[r][1] = static_cast<float*>(ptrs[7]);
+    h->peer_din[r][0] = (r == me || rec[r * kP2PBuffers + 6].kind == 1) ? static_cast<float*>(ptrs[6]) : nullptr;
+    h->peer_din[r][1] = (r == me || rec[r * kP2PBuffers + 7].kind == 1) ? static_cast<float*>(ptrs[7]) : nullptr;
     if (r == 0) {
       h->peerHh0 = static_cast<float2*>(ptrs[2]);
       h->peer_xout0[0] = static_cast<float*>(ptrs[3]);
       h->peer_xout0[1] = static_cast<float*>(ptrs[4]);
     }
   }
+  h->din_records.assign(reinterpret_cast<const unsigned char*>(all_blobs),
+                        reinterpret_cast<const unsigned char*>(all_blobs) + (size_t)G * kP2PBuffers * sizeof(P2PRecord));
   h->p2p_on = true;
   return B200CONV_OK;
 }
@@ -1521,7 +1525,32 @@ int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
 int b200conv_p2p_set_input_broadcast(b200conv_t* h, int enable) {
   if (!h) return B200CONV_EINVAL;
   if (enable && !h->p2p_on) return fail(h, B200CONV_ESTATE, "input broadcast needs an attached slot exchange");
+#if !defined(PC_EMULATE)
+  if (enable && h->cfg.shard_rank == 0) {      // map the peers' staging buffers now (cross-process: CUDA IPC)
+    if (int rc = set_device(h)) return rc;
+    const P2PRecord* rec = reinterpret_cast<const P2PRecord*>(h->din_records.data());
+    for (int r = 1; r < h->cfg.shard_count; ++r)
+      for (int i = 0; i < 2; ++i) {
+        if (h->peer_din[r][i]) continue;
+        const P2PRecord& x = rec[r * kP2PBuffers + 6 + i];
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, x.ipc, 64);
+        void* p = nullptr;
+        CU_CHECK(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(p);
+        h->peer_din[r][i] = static_cast<float*>(p);
+      }
+  }
+#endif
   h->bcast_in = enable != 0;
+  return B200CONV_OK;
+}
+
+int b200conv_p2p_detach(b200conv_t* h) {
+  if (!h) return B200CONV_EINVAL;
+  if (h->s_main) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->s_main); if (h->s_post) cudaStreamSynchronize(h->s_post); }
+  h->p2p_on = false;
+  h->bcast_in = false;
   return B200CONV_OK;
 }
 

@@ -299,24 +299,15 @@ def main():
             attach_reduce(eng, device=local)          # NCCL reduce hook (always installed)
             mgpu_path = "partition-range shards + NCCL reduce of partial spectra to rank 0"
             if args.mgpu == "p2p":
-                ok, why = 1, ""
-                try:
-                    attach_p2p(eng)                   # fused slot exchange over NVLink peer memory
-                    if args.e2e_bcast:                # host-pointer path: only rank 0 crosses PCIe
-                        eng.p2p_set_input_broadcast(True)
-                except Exception as ex:               # both are GPU paths; say which one ran
-                    ok, why = 0, str(ex)
-                    print(f"[bench] p2p attach failed on rank {rank}: {ex}", file=sys.stderr)
-                # every shard has to take the same path: agree on it
-                flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if int(flag.item()) == 1:
+                ok, why = attach_p2p(eng)             # fused slot exchange over NVLink peer memory (same answer on every rank)
+                if ok:
                     mgpu_path = ("partition-range shards + fused slot exchange: sweep epilogue stores partial rows into "
                                  "the owner GPU's slot over NVLink, flag barrier, per-slice inverse FFT (no NCCL on the data path)")
+                    if args.e2e_bcast:                # host-pointer path: only rank 0 crosses PCIe
+                        eng.p2p_set_input_broadcast(True)
                 else:
-                    if ok:
-                        eng.p2p_detach()
-                    mgpu_path += " (slot exchange not available on every rank" + (f": {why}" if why else "") + ")"
+                    print(f"[bench] slot exchange not available ({why}); using the NCCL reduce path", file=sys.stderr)
+                    mgpu_path += f" (slot exchange not available: {why})"
 
         x_host = torch.empty((C, n), dtype=torch.float32).pin_memory()
         for c in range(C):

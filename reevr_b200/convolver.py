@@ -190,11 +190,19 @@ class Engine:
                     return -1
             self._barrier_cb = _lib.BARRIER_FN(tramp)
             self._l.b200conv_p2p_set_host_barrier(self._h, self._barrier_cb, None)
+        blobs = allgather(self.p2p_export(mode))
+        self.p2p_import(blobs)
+
+    def p2p_export(self, mode: int = 0) -> bytes:
         n = self._l.b200conv_p2p_blob_size(self._h)
         blob = C.create_string_buffer(n)
         self._check(self._l.b200conv_p2p_export(self._h, blob, mode), "p2p_export")
-        blobs = allgather(blob.raw)
-        joined = C.create_string_buffer(b"".join(blobs), n * len(blobs))
+        return blob.raw
+
+    def p2p_import(self, blobs) -> None:
+        """blobs: every shard's exported blob, in rank order."""
+        data = b"".join(blobs)
+        joined = C.create_string_buffer(data, len(data))
         self._check(self._l.b200conv_p2p_import(self._h, joined), "p2p_import")
 
     def p2p_detach(self):

@@ -52,11 +52,30 @@ def attach_reduce(engine, device: int | None = None, group=None, root: int = 0) 
     engine.set_reduce(hook)
 
 
-def attach_p2p(engine, group=None) -> None:
-    """Enables the fused slot-exchange path on a sharded uniform Engine: all-gathers the CUDA IPC
-    blobs of every rank with torch.distributed (plumbing only — the data path makes no NCCL call)."""
-    def allgather(blob: bytes):
-        out = [None] * dist.get_world_size(group)
-        dist.all_gather_object(out, blob, group=group)
-        return out
-    engine.p2p_attach(allgather, mode=0)
+def attach_p2p(engine, group=None) -> tuple:
+    """Enables the fused slot-exchange path on a sharded uniform Engine.  torch.distributed only moves the
+    CUDA IPC blobs (plumbing) — the data path makes no NCCL call.  Every rank executes the same collectives
+    whether or not its own export / import works, and all ranks end on the SAME path:
+    returns (True, "") if the exchange is active everywhere, else (False, reason) with the exchange detached."""
+    world = dist.get_world_size(group)
+    blob, err = None, ""
+    try:
+        blob = engine.p2p_export(mode=0)
+    except Exception as ex:                       # e.g. CUDA IPC not permitted in this container
+        err = f"export: {ex}"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (blob, err), group=group)
+    if all(b is not None for b, _ in gathered):
+        try:
+            engine.p2p_import([b for b, _ in gathered])
+        except Exception as ex:
+            err = f"import: {ex}"
+    else:
+        err = err or next(e for b, e in gathered if b is None)
+    oks = [None] * world
+    dist.all_gather_object(oks, err, group=group)
+    bad = [e for e in oks if e]
+    if bad:
+        engine.p2p_detach()
+        return False, bad[0]
+    return True, ""

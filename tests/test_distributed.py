@@ -38,6 +38,11 @@ def _worker(rank, world, port, kind, q):
     else:
         assert e.init_twostage(16, 256, [h])
     attach_reduce(e)
+    if kind == "twostage":
+        # the slot exchange refuses multi-stage handles: every rank must learn that and stay on the reduce hook
+        from reevr_b200.distributed import attach_p2p
+        ok, why = attach_p2p(e)
+        assert not ok and "single-stage" in why
     st = e.stages()
     ys = [e.process([x[i:i + 1000]])[0] for i in range(0, x.size, 1000)]
     y = np.concatenate(ys)

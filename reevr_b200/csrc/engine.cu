@@ -40,7 +40,7 @@
 
 namespace {
 
-constexpr int kDPre = 4;          // max prefetch distance of the CMAC kernels (rows readable past the end)
+constexpr int kDPre = 8;          // max prefetch distance of the CMAC kernels (rows readable past the end)
 constexpr int kPadP = 32;         // H / history rows are padded to a multiple of this
 constexpr int kMaxTT = 32;        // slack rows after the newest X row
 constexpr int kDefaultBatch = 4736;   // 148 SMs * 32
@@ -466,6 +466,9 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     case 26: launch_cmac2_bs<8, 4, 4, 4>(h, P, C); break;
     case 27: launch_cmac2_bs<16, 4, 2, 8>(h, P, C); break;    // 64 thr/CTA
     case 28: launch_cmac2_bs<24, 4, 4, 2>(h, P, C); break;
+    // banked for the next tuning round (functionally verified, not yet timed):
+    case 33: launch_cmac2_bs<16, 8, 4, 3>(h, P, C); break;    // deeper software prefetch
+    case 34: launch_cmac2_bs<16, 4, 2, 6>(h, P, C); break;    // 64-thread CTAs, 6 per SM: finer load balance
     default: return fail(h, B200CONV_EINVAL, "unknown cmac_variant");
   }
   timing_end(h, id);

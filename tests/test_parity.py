@@ -244,7 +244,7 @@ def test_long_call_is_split_into_groups(lib):
     assert peak_err(y, o.run(x, 64)) <= TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 11, 12, 16, 21, 22, 23, 24, 25, 26, 27, 28])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 11, 12, 16, 21, 22, 23, 24, 25, 26, 27, 28, 33, 34])
 def test_cmac_variants(lib, variant):
     h = orc.synth_ir(3000)
     x = orc.synth_input(64 * 100)

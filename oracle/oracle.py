@@ -58,6 +58,10 @@ def _load_oracle() -> C.CDLL:
     lib.oc_twostage_init.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t]
     lib.oc_naive_convolve.restype = None
     lib.oc_naive_convolve.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p]
+    lib.oc_apply_decay.restype = None
+    lib.oc_apply_decay.argtypes = [_f32p, C.c_size_t, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.c_double]
+    lib.oc_decay_window.restype = None
+    lib.oc_decay_window.argtypes = [_f32p]
     lib.oc_uniform_partitions.restype = C.c_size_t
     lib.oc_uniform_partitions.argtypes = [C.c_void_p]
     lib.oc_uniform_block.restype = C.c_size_t
@@ -197,6 +201,22 @@ class RefUniform(OracleUniform):
 class RefTwoStage(OracleTwoStage):
     """The unmodified reference TwoStageFFTConvolver (oracle/_ref)."""
     _which = "ref"
+
+
+def apply_decay(ir, lut, srate: float) -> np.ndarray:
+    """C restatement of Impulse::applyDecay (src/dsp/Impulse.cpp:602-648); lut has 2049 entries."""
+    buf = np.array(ir, dtype=np.float32, copy=True)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    assert lut.size == 2049
+    if buf.size:
+        _lib("oc").oc_apply_decay(buf, buf.size, lut, float(srate))
+    return buf
+
+
+def decay_window() -> np.ndarray:
+    w = np.empty(4096, np.float32)
+    _lib("oc").oc_decay_window(w)
+    return w
 
 
 def naive_convolve(x, h) -> np.ndarray:

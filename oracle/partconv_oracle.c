@@ -423,3 +423,64 @@ void oc_naive_convolve(const float* in, size_t inLen, const float* ir, size_t ir
 /* Introspection used by tests (post-trim partition count etc.) */
 size_t oc_uniform_partitions(const oc_uniform* c) { return c->count; }
 size_t oc_uniform_block(const oc_uniform* c) { return c->block; }
+
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8f-3 groundwork (NOT on the round-1 hot path): the FFT-heavy core of the IR shaping,
+ * Impulse::applyDecay (src/dsp/Impulse.cpp:602-648) — a 4096-point STFT with hop 1024
+ * (Impulse.h:21-22), the Blackman-type analysis window of Impulse.cpp:65-69, a per-bin decay that
+ * compounds once per block after the early-reflection blocks (:612, :626-633) and an overlap-add
+ * normalised by the summed window (:637-647).  Parity status: UNPINNED — Impulse.cpp needs JUCE and
+ * cannot be compiled here, so this restatement is only checked through properties
+ * (tests/test_oracle.py: unit LUT reproduces the input, independent float64 numpy model).
+ * ---------------------------------------------------------------------------------------- */
+#define OC_STFT_N 4096
+#define OC_STFT_HOP (OC_STFT_N / 4)
+
+void oc_decay_window(float* w) {                         /* Impulse.cpp:65-69 */
+  const float step = 2.0f * 3.14159265358979323846f / (float)OC_STFT_N;
+  for (int i = 0; i < OC_STFT_N / 2; ++i)
+    w[i] = 0.42f - 0.50f * cosf((float)i * step) + 0.08f * cosf(2.0f * (float)i * step);
+  for (int i = OC_STFT_N / 2; i < OC_STFT_N; ++i) w[i] = w[OC_STFT_N - 1 - i];
+}
+
+/* buf[n] in place; lut[OC_STFT_N/2 + 1] per-bin decay per block; srate as in the reference */
+void oc_apply_decay(float* buf, size_t n, const double* lut, double srate) {
+  if (n == 0) return;
+  const size_t nblocks = (n + OC_STFT_HOP - 1) / OC_STFT_HOP;                       /* :604 */
+  const int K = OC_STFT_N / 2 + 1;
+  float* window = (float*)malloc(OC_STFT_N * sizeof(float));
+  float* block = (float*)malloc(OC_STFT_N * sizeof(float));
+  float* re = (float*)malloc(K * sizeof(float));
+  float* im = (float*)malloc(K * sizeof(float));
+  float* out = (float*)calloc(n, sizeof(float));
+  float* norm = (float*)calloc(n, sizeof(float));
+  double* acc = (double*)malloc(K * sizeof(double));
+  for (int k = 0; k < K; ++k) acc[k] = 1.0;
+  oc_decay_window(window);
+  oc_fft f; memset(&f, 0, sizeof(f));
+  oc_fft_init(&f, OC_STFT_N);
+  const int skip = (int)ceil(100.0 * srate / (1000.0 * (double)OC_STFT_N));         /* :612, EARLY_REFLECTIONS_MS = 100 (Globals.h:34) */
+  for (size_t b = 0; b < nblocks; ++b) {
+    const size_t start = b * OC_STFT_HOP;
+    size_t bs = n - start < (size_t)OC_STFT_N ? n - start : (size_t)OC_STFT_N;      /* :618 */
+    memset(block, 0, OC_STFT_N * sizeof(float));
+    for (size_t i = 0; i < bs; ++i) block[i] = buf[start + i] * window[i];          /* :620-621 */
+    oc_rfft(&f, block, re, im);                                                     /* :623 */
+    if ((long long)b > (long long)skip)                                             /* :626 */
+      for (int k = 1; k < K; ++k) {
+        const double d = acc[k] * lut[k];
+        acc[k] = d;
+        re[k] *= (float)d;
+        im[k] *= (float)d;
+      }
+    oc_irfft(&f, block, re, im);                                                    /* :635 */
+    for (size_t i = 0; i < bs; ++i) {                                               /* :637-644 */
+      out[start + i] += block[i];
+      norm[start + i] += window[i];
+    }
+  }
+  for (size_t i = 0; i < n; ++i) buf[i] = norm[i] > 0.0f ? out[i] / norm[i] : 0.0f; /* :646-648 */
+  oc_fft_free(&f);
+  free(window); free(block); free(re); free(im); free(out); free(norm); free(acc);
+}

@@ -99,3 +99,45 @@ def test_golden_fixture(path):
     y = run_case(spec, impl="oracle")
     assert y.shape == g["out"].shape
     assert _peak_err(y, g["out"]) <= 1e-6
+
+
+def test_apply_decay_restatement_properties():
+    """Groundwork for SURVEY 8f-3 (IR shaping on the device, a 'next' row): the STFT decay of
+    src/dsp/Impulse.cpp:602-648.  Unpinned (Impulse.cpp needs JUCE): checked against an independent float64
+    numpy model and through the identity property."""
+    sr = 48000.0
+    h = orc.synth_ir(30000)
+    # (1) unit LUT: windowed overlap-add divided by the summed window reproduces the input
+    # (the very first samples are ill-conditioned in the reference itself: the window starts at 0, so sample 0
+    #  comes back as 0 and the next few are divided by a tiny window sum, Impulse.cpp:646-648)
+    y = orc.apply_decay(h, np.ones(2049), sr)
+    assert y[0] == 0.0
+    assert np.max(np.abs(y[64:1024] - h[64:1024])) <= 1e-4 * np.max(np.abs(h))
+    assert np.max(np.abs(y[1024:] - h[1024:])) <= 2e-6 * np.max(np.abs(h))
+    # (2) frequency-dependent decay vs an independent float64 model
+    lut = np.linspace(1.0, 0.7, 2049)
+    w = orc.decay_window().astype(np.float64)
+    N, hop = 4096, 1024
+    n = h.size
+    out = np.zeros(n)
+    norm = np.zeros(n)
+    skip = int(np.ceil(100 * sr / (1000.0 * N)))
+    nblocks = (n + hop - 1) // hop
+    for b in range(nblocks):
+        s0 = b * hop
+        bs = min(N, n - s0)
+        blk = np.zeros(N)
+        blk[:bs] = h[s0:s0 + bs].astype(np.float64) * w[:bs]
+        X = np.fft.rfft(blk)
+        if b > skip:
+            g = lut ** (b - skip)
+            g[0] = 1.0
+            X = X * g
+        yb = np.fft.irfft(X, N)
+        out[s0:s0 + bs] += yb[:bs]
+        norm[s0:s0 + bs] += w[:bs]
+    want = np.where(norm > 0, out / np.where(norm > 0, norm, 1), 0.0)
+    got = orc.apply_decay(h, lut, sr)
+    assert np.max(np.abs(got[64:1024] - want[64:1024])) <= 1e-4 * np.max(np.abs(want))
+    assert np.max(np.abs(got[1024:] - want[1024:])) <= 1e-5 * np.max(np.abs(want))
+    assert np.sum(got[-8000:] ** 2) < 0.2 * np.sum(h[-8000:] ** 2)      # the tail really decays faster

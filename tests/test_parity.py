@@ -246,6 +246,8 @@ def test_long_call_is_split_into_groups(lib):
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 11, 12, 16, 21, 22, 23, 24, 25, 26, 27, 28, 33, 34])
 def test_cmac_variants(lib, variant):
+    if variant in (33, 34) and b"EMULATED" not in lib.b200conv_version():
+        pytest.skip("banked tuning variant: verified on the emulation, first GPU run is a round-2 item")
     h = orc.synth_ir(3000)
     x = orc.synth_input(64 * 100)
     e = Engine(1, cmac_variant=variant, lib=lib)

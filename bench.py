@@ -48,6 +48,9 @@ WORKLOADS = {
     "ir1": dict(C=1, ir_s=1, sr=48000, block=512, desc="mono 48 kHz, 1 s IR, uniform block 512 (config 1)"),
     "ch8": dict(C=8, ir_s=10, sr=48000, block=512, desc="8-channel 48 kHz, 10 s IR per channel, block 512 (config 4)"),
     "ir120": dict(C=2, ir_s=120, sr=48000, block=512, desc="stereo 48 kHz, 120 s IR, uniform block 512 (config 5)"),
+    # two-stage shapes (head block = `block`, tail block = `tail`): not bench lines of the contract, kept for tuning runs
+    "cfg2": dict(C=2, ir_s=5, sr=48000, block=128, tail=8192, desc="stereo 48 kHz, 5 s IR, two-stage head 128 / tail 8192 (config 2)"),
+    "cfg3": dict(C=2, ir_s=30, sr=96000, block=64, tail=8192, desc="stereo 96 kHz, 30 s IR, two-stage head 64 / tail 8192 (config 3)"),
 }
 
 
@@ -288,7 +291,10 @@ def main():
         eng = Engine(C, device=local, max_batch_blocks=gb + 1, shard_rank=rank, shard_count=world, cmac_variant=args.variant)
         irs = [synth_ir(L, c) for c in range(C)]
         t_init = time.perf_counter()
-        assert eng.init_uniform(block, irs)
+        if "tail" in wl:
+            assert eng.init_twostage(block, wl["tail"], irs)
+        else:
+            assert eng.init_uniform(block, irs)
         t_init = time.perf_counter() - t_init
         st = eng.stages()[0]
         P = int(st["partitions"])
@@ -369,9 +375,16 @@ def main():
         peak, peak_kind = measured_peaks()
         per_launch_ms = cm_ms / max(cm_n, 1)
         blocks_per_launch = T * reps / max(cm_n, 1)
-        alg_bytes_launch = algorithmic_bytes_per_channel_block(Ploc, block) * C * blocks_per_launch
+        stages_all = eng.stages()
+        if len(stages_all) == 1:
+            alg_bytes_launch = algorithmic_bytes_per_channel_block(Ploc, block) * C * blocks_per_launch
+            ffma = 4.0 * Ploc * block * C * blocks_per_launch      # 4 FP32 FMA per complex MAC, B bins per row
+        else:   # multi-stage: SURVEY 8d, sum over stages of the per-sample figures, spread over the sweep launches
+            per_sample = sum(algorithmic_bytes_per_channel_block(int(x["p_end"]) - int(x["p_begin"]), int(x["block"])) / int(x["block"])
+                             for x in stages_all)
+            alg_bytes_launch = per_sample * C * n * reps / max(cm_n, 1)
+            ffma = sum(4.0 * (int(x["p_end"]) - int(x["p_begin"])) for x in stages_all) * C * n * reps / max(cm_n, 1)
         achieved = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
-        ffma = 4.0 * Ploc * block * C * blocks_per_launch      # 4 FP32 FMA per complex MAC, B bins per row
         fp32_tflops = 2.0 * ffma / (per_launch_ms * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         traffic = None
@@ -426,7 +439,7 @@ def main():
     WL0 = wl
     # one step = one batch of T blocks of the same stereo stream, identical at every N (strong scaling):
     # 28416 blocks = 14.5 M frames = 5 min of audio; at N = 8 each GPU still sweeps ~0.5 ms per step
-    T = args.blocks or (28416 if args.workload == "metric" else 7104)
+    T = args.blocks or (28416 if args.workload == "metric" else (7104 * 512 // wl["block"] if "tail" in wl else 7104))
     main_res = run_workload(wl, T, args.steps, with_e2e=not args.no_e2e, with_clocks=True)
     extra = None
     if args.also_ir120 and args.workload == "metric":

@@ -152,6 +152,13 @@ int    b200conv_p2p_set_input_broadcast(b200conv_t* h, int enable);
 typedef int (*b200conv_barrier_fn)(void* user);
 int    b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* user);
 
+/* SURVEY 8f-3 (a "next" row, not part of the hot path): the STFT decay-EQ of the IR shaping,
+ * Impulse::applyDecay (src/dsp/Impulse.cpp:602-648), on the device: `ir` (host, n float32 taps) is
+ * processed in place; lut = 2049 per-bin decay factors per STFT block (Impulse.cpp:566-590 builds them
+ * on the host from the EQ bands); srate as in the reference (sets the early-reflection blocks that are
+ * left untouched).  Stand-alone call: no handle, own temporary device buffers. */
+int b200conv_ir_decay_eq(int device, float* ir, size_t n, const double* lut, double srate);
+
 /* Pinned host memory helpers (staging buffers for the e2e path). */
 void* b200conv_alloc_host(size_t bytes);
 void  b200conv_free_host(void* p);

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200conv.so")
-SOURCES = ["engine.cu"]
-DEPS = ["engine.cu", "kernels.cuh", os.path.join("..", "..", "include", "b200conv.h")]
+SOURCES = ["engine.cu", "irshape.cu"]
+DEPS = ["engine.cu", "irshape.cu", "kernels.cuh", os.path.join("..", "..", "include", "b200conv.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -225,6 +225,19 @@ class Engine:
             pass
 
 
+def ir_decay_eq(ir, lut, srate: float, device: int = 0, lib=None) -> np.ndarray:
+    """Device version of Impulse::applyDecay (src/dsp/Impulse.cpp:602-648): returns the shaped IR."""
+    lib = lib or _lib.default()
+    buf = np.array(ir, dtype=np.float32, copy=True)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    if lut.size != 2049:
+        raise ValueError("lut needs 2049 entries (4096-point STFT)")
+    rc = lib.b200conv_ir_decay_eq(device, buf.ctypes.data, buf.size, lut.ctypes.data, float(srate))
+    if rc != 0:
+        raise B200ConvError(f"b200conv_ir_decay_eq failed ({rc})")
+    return buf
+
+
 class FFTConvolver:
     """Uniform partitioned convolver, one channel (reference: FFTConvolver.h:62-80)."""
 

@@ -897,7 +897,7 @@ struct BarrierParams {
   unsigned int epoch;
 };
 
-__global__ void k_p2p_barrier(BarrierParams P) {
+static __global__ void k_p2p_barrier(BarrierParams P) {
   const int t = threadIdx.x;
   if (t >= P.G) return;
   __threadfence_system();                      // everything this GPU wrote before the barrier is visible first
@@ -923,7 +923,7 @@ struct MixParams {
   float mix[64];
 };
 
-__global__ void k_mix(MixParams P) {
+static __global__ void k_mix(MixParams P) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int o = blockIdx.y;
   if (i >= P.n) return;
@@ -937,7 +937,7 @@ __global__ void k_mix(MixParams P) {
 
 // crossfade of two convolver outputs on the device (IR hot-swap, src/PluginProcessor.cpp:1800-1830):
 // dst[c][i] = (1 - a_i) * a[c][i] + a_i * b[c][i],  a_i = clamp(alpha0 + i*step, 0, 1); grid (ceil(n/256), C)
-__global__ void k_xfade(float* dst, const float* a, const float* b, long long stride, long long n, float alpha0, float step) {
+static __global__ void k_xfade(float* dst, const float* a, const float* b, long long stride, long long n, float alpha0, float step) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long o = (long long)blockIdx.y * stride + i;
@@ -947,7 +947,7 @@ __global__ void k_xfade(float* dst, const float* a, const float* b, long long st
 
 // strided row copy on the SMs (rows x width floats); used where a copy-engine copy queued behind a spinning
 // flag barrier would block the H2D copies of the following launch groups (slot-exchange path)
-__global__ void k_copy_rows(float* dst, long long dpitch, const float* src, long long spitch, long long width, int rows) {
+static __global__ void k_copy_rows(float* dst, long long dpitch, const float* src, long long spitch, long long width, int rows) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   if (i < width && r < rows) dst[(long long)r * dpitch + i] = src[(long long)r * spitch + i];

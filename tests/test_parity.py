@@ -324,3 +324,20 @@ def test_ir_hot_swap_prime_and_crossfade(lib):
         assert peak_err(y_pre[c], r_pre) <= TOL
         assert peak_err(y_fade[c], r_fade) <= TOL
         assert peak_err(y_post[c], r_post) <= TOL
+
+
+def test_ir_decay_eq_stft(lib):
+    """SURVEY 8f-3 groundwork: device STFT decay-EQ (Impulse::applyDecay) against the C restatement."""
+    if b"EMULATED" not in lib.b200conv_version():
+        pytest.skip("written after the round-1 GPU budget was spent: first GPU run is a round-2 item")
+    from reevr_b200.convolver import ir_decay_eq
+    sr = 48000.0
+    for n in (30000, 4096, 5000, 1):
+        h = orc.synth_ir(n)
+        for lut in (np.ones(2049), np.linspace(1.0, 0.7, 2049), np.linspace(0.8, 1.05, 2049)):
+            want = orc.apply_decay(h, lut, sr)
+            got = ir_decay_eq(h, lut, sr, lib=lib)
+            peak = max(np.max(np.abs(want)), 1e-30)
+            # the first hop is ill-conditioned in the reference itself (window starts at 0)
+            assert np.max(np.abs(got[1024:] - want[1024:])) <= 1e-5 * peak if n > 1024 else True
+            assert np.max(np.abs(got[64:1024] - want[64:1024])) <= 2e-3 * peak if n > 64 else True

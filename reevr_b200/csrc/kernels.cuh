@@ -4,9 +4,10 @@
 //                                                         (FFTConvolver.cpp:172-173, AudioFFT.cpp:114-137);
 //                                                         the same kernel builds the IR spectra H[p]
 //                                                         (FFTConvolver::init, FFTConvolver.cpp:129-137)
-//   K2 k_cmac_batch   Y[t]  = sum_p H[p] (.) X[t-p]       replaces the ComplexMultiplyAccumulate sweep over
-//                                                         the frequency-domain delay line
-//                                                         (FFTConvolver.cpp:176-187, Utilities.cpp:62-111)
+//   K2 k_cmac_batch2  Y[t]  = sum_p H[p] (.) X[t-p]       replaces the ComplexMultiplyAccumulate sweep over
+//      (batched, FFMA2; k_cmac_batch = scalar A/B variant)   the frequency-domain delay line
+//   K2s k_cmac_stream_rows  same sum, one block per launch,  (FFTConvolver.cpp:176-187, Utilities.cpp:62-111)
+//      memory-bound (k_cmac_stream: generic fallback, B < 64)
 //   K3 k_inv_fft_ola  y_t   = IRFFT_2B(Y[t] + (-1)^k Y[t-1])[0:B] (+ look-ahead stage outputs)
 //                                                         replaces AudioFFT::ifft + Sum + overlap save
 //                                                         (FFTConvolver.cpp:190-204, AudioFFT.cpp:139-159,
@@ -18,9 +19,12 @@
 // entry 0 packs the two purely real bins as (DC, Nyquist), entries 1..B-1 are bins 1..B-1.
 // Rows are therefore B*8 bytes — a power of two, 32-byte-sector aligned for every B >= 4.
 //
+// Also here: the multi-GPU slot-exchange pieces (cmac_store epilogue, sum_partials, k_p2p_barrier), the
+// device mixdown / crossfade / row-copy helpers (k_mix, k_xfade, k_copy_rows).
+//
 // The per-thread / per-phase bodies are plain inline functions so that tests/emu (g++) can run
 // the identical index arithmetic on the CPU; the __global__ wrappers only add the thread
-// geometry and the __syncthreads() between phases.
+// geometry and the barriers between phases.
 #pragma once
 
 #if defined(__CUDACC__)

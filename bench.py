@@ -450,31 +450,55 @@ def main():
     # the memory-bound form of the sweep (real-time path, one block per launch) on a working set beyond L2:
     # this is the kernel whose "% of HBM roofline" is a bandwidth statement
     stream_roof = None
+    realtime = None
     if world == 1 and not args.no_stream:
-        wl5 = WORKLOADS["ir120"]
-        C5, B5 = wl5["C"], wl5["block"]
-        e5 = Engine(C5, device=local)
-        assert e5.init_uniform(B5, [synth_ir(wl5["ir_s"] * wl5["sr"], c) for c in range(C5)])
-        P5 = int(e5.stages()[0]["partitions"])
-        xs5 = torch.from_numpy(np.stack([synth_input(B5 * 72, c) for c in range(C5)])).cuda()
-        y5 = torch.empty((C5, B5), device="cuda")
-        for i in range(8):
-            e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
-        e5.set_timing(True)
-        ts5 = []
-        for i in range(8, 72):
-            e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
-            ts5.append(e5.last_timing()["cmac_ms"])
-        e5.close()
-        t5 = statistics.median(ts5)
-        bytes5 = 16 * P5 * (B5 + 1) * C5                      # every H and FDL row read once per block step
-        peak, peak_kind = measured_peaks()
-        stream_roof = {"kernel": "k_cmac_stream_rows (one 512-sample block per launch)", "workload": wl5["desc"],
-                       "working_set_bytes": 2 * P5 * B5 * 8 * C5, "bound": "hbm", "launch_ms": t5,
-                       "achieved": bytes5 / (t5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": bytes5 / (t5 * 1e-3) / 1e9 / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                       "algorithmic_bytes_per_launch": bytes5, "traffic": 188137728,
-                       "traffic_source": "profiles/r01_prof_final_stream_cfg5.txt (ncu: 184.35 MB read + 3.79 MB written)"}
+        try:    # secondary legs: never let them take the headline line down
+            wl5 = WORKLOADS["ir120"]
+            C5, B5 = wl5["C"], wl5["block"]
+            e5 = Engine(C5, device=local)
+            assert e5.init_uniform(B5, [synth_ir(wl5["ir_s"] * wl5["sr"], c) for c in range(C5)])
+            P5 = int(e5.stages()[0]["partitions"])
+            xs5 = torch.from_numpy(np.stack([synth_input(B5 * 72, c) for c in range(C5)])).cuda()
+            y5 = torch.empty((C5, B5), device="cuda")
+            for i in range(8):
+                e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
+            e5.set_timing(True)
+            ts5 = []
+            for i in range(8, 72):
+                e5.process_device(xs5[:, i * B5:].data_ptr(), xs5.shape[1], y5.data_ptr(), B5, B5, sync=True)
+                ts5.append(e5.last_timing()["cmac_ms"])
+            e5.close()
+            t5 = statistics.median(ts5)
+            bytes5 = 16 * P5 * (B5 + 1) * C5                      # every H and FDL row read once per block step
+            peak, peak_kind = measured_peaks()
+            stream_roof = {"kernel": "k_cmac_stream_rows (one 512-sample block per launch)", "workload": wl5["desc"],
+                           "working_set_bytes": 2 * P5 * B5 * 8 * C5, "bound": "hbm", "launch_ms": t5,
+                           "achieved": bytes5 / (t5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": bytes5 / (t5 * 1e-3) / 1e9 / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                           "algorithmic_bytes_per_launch": bytes5, "traffic": 188137728,
+                           "traffic_source": "profiles/r01_prof_final_stream_cfg5.txt (ncu: 184.35 MB read + 3.79 MB written)"}
+        except Exception as ex:
+            stream_roof = {"error": f"{type(ex).__name__}: {ex}"}
+        try:    # the real-time call a plugin makes: host pointers, one 512-sample block per call, synchronous
+            C0, B0 = wl["C"], wl["block"]
+            e0 = Engine(C0, device=local)
+            assert e0.init_uniform(B0, [synth_ir(wl["ir_s"] * wl["sr"], c) for c in range(C0)])
+            blk = [synth_input(B0, c) for c in range(C0)]
+            for _ in range(50):
+                e0.process(blk)
+            lat = []
+            for _ in range(300):
+                t0 = time.perf_counter()
+                e0.process(blk)
+                lat.append(time.perf_counter() - t0)
+            e0.close()
+            med = statistics.median(lat)
+            realtime = {"call": "b200conv_process(), host pointers, len = block = 512, synchronous", "median_us": med * 1e6,
+                        "p99_us": sorted(lat)[int(0.99 * len(lat))] * 1e6, "value": B0 / med / 1e6,
+                        "unit": "M stereo frames/s" if C0 == 2 else f"M {C0}-channel frames/s",
+                        "note": "latency-bound (PCIe + 3 launches per call), reported for completeness — SURVEY 8d"}
+        except Exception as ex:
+            realtime = {"error": f"{type(ex).__name__}: {ex}"}
 
     if args.sweep and rank == 0 and world == 1:
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--blocks", str(T)], stdout=sys.stderr)
@@ -499,6 +523,8 @@ def main():
             line["ir120"] = extra
         if stream_roof:
             line["roofline_stream"] = stream_roof
+        if realtime:
+            line["realtime_process"] = realtime
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

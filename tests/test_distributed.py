@@ -192,8 +192,7 @@ def test_slot_exchange_in_process(backend, G):
         assert np.max(np.abs(y - yo)) / np.max(np.abs(yo)) <= TOL, chunks
 
 
-# (emulation only for now: the broadcast is off by default and has not been run on a GPU box yet — round 2)
-@pytest.mark.parametrize("backend,G", [("emu", 2), ("emu", 4)])
+@pytest.mark.parametrize("backend,G", [("emu", 2), ("emu", 4), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
 def test_slot_exchange_input_broadcast(backend, G):
     """Host-pointer calls with the input broadcast: only shard 0 uploads, the peers get every launch group
     through their staging buffers (they are fed garbage here) — short latency-path calls and long pipelined ones."""

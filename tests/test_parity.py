@@ -246,8 +246,6 @@ def test_long_call_is_split_into_groups(lib):
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 11, 12, 16, 21, 22, 23, 24, 25, 26, 27, 28, 33, 34])
 def test_cmac_variants(lib, variant):
-    if variant in (33, 34) and b"EMULATED" not in lib.b200conv_version():
-        pytest.skip("banked tuning variant: verified on the emulation, first GPU run is a round-2 item")
     h = orc.synth_ir(3000)
     x = orc.synth_input(64 * 100)
     e = Engine(1, cmac_variant=variant, lib=lib)
@@ -328,8 +326,6 @@ def test_ir_hot_swap_prime_and_crossfade(lib):
 
 def test_ir_decay_eq_stft(lib):
     """SURVEY 8f-3 groundwork: device STFT decay-EQ (Impulse::applyDecay) against the C restatement."""
-    if b"EMULATED" not in lib.b200conv_version():
-        pytest.skip("written after the round-1 GPU budget was spent: first GPU run is a round-2 item")
     from reevr_b200.convolver import ir_decay_eq
     sr = 48000.0
     for n in (30000, 4096, 5000, 1):

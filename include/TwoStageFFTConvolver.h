@@ -40,7 +40,12 @@ public:
       b200conv_stage_info info;
       if (b200conv_stage(h, 1, &info) == B200CONV_OK)
       {
-        _tailBlockSize = info.block;
+        // hook cadence = the tail block size the caller asked for, rounded like the reference does
+        // (TwoStageFFTConvolver.cpp:100-104,118); the engine may use smaller partitions internally
+        size_t t = headBlockSize > tailBlockSize ? headBlockSize : tailBlockSize;
+        size_t p = 1;
+        while (p < t) p *= 2;
+        _tailBlockSize = p > info.block ? p : info.block;
         _hasTail = true;
       }
     }

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -41,7 +42,7 @@
 namespace {
 
 constexpr int kDPre = 8;          // max prefetch distance of the CMAC kernels (rows readable past the end)
-constexpr int kPadP = 32;         // H / history rows are padded to a multiple of this
+constexpr int kPadP = 96;         // H / history rows are padded to a multiple of this = lcm of every sweep tile height TT in use (8, 12, 16, 24, 32)
 constexpr int kMaxTT = 32;        // slack rows after the newest X row
 constexpr int kDefaultBatch = 4736;   // 148 SMs * 32
 constexpr int kMaxBlockLog2 = 13;     // B <= 8192 (two M-point ping-pong buffers = 128 KB smem)
@@ -143,14 +144,39 @@ struct b200conv {
 
 namespace {
 
+// Only errors that poison the CUDA context (or mean there is no usable device) make the handle fail for
+// good; everything else — out of memory while loading a long IR, CUDA IPC not permitted in this container,
+// an invalid argument — is cleared from the runtime, reported through the status code and leaves the
+// handle usable (the caller can fall back to the reduce hook, load a shorter IR, ...).
+bool cuda_error_is_sticky(cudaError_t e) {
+#if defined(PC_EMULATE)
+  (void)e;
+  return false;
+#else
+  switch (e) {
+    case cudaErrorIllegalAddress: case cudaErrorLaunchFailure: case cudaErrorLaunchTimeout:
+    case cudaErrorIllegalInstruction: case cudaErrorMisalignedAddress: case cudaErrorInvalidAddressSpace:
+    case cudaErrorInvalidPc: case cudaErrorHardwareStackError: case cudaErrorAssert:
+    case cudaErrorECCUncorrectable: case cudaErrorNoDevice: case cudaErrorInsufficientDriver:
+    case cudaErrorDevicesUnavailable: case cudaErrorCudartUnloading: case cudaErrorUnknown:
+      return true;
+    default:
+      return false;
+  }
+#endif
+}
+
+int cuda_fail(b200conv* h, cudaError_t e, const char* what) {
+  h->err = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();                                   // clear the runtime's (non-sticky) last error
+  if (cuda_error_is_sticky(e)) h->sticky_cuda_error = true;
+  return e == cudaErrorMemoryAllocation ? B200CONV_ENOMEM : B200CONV_ECUDA;
+}
+
 #define CU_CHECK(h, expr)                                                                  \
   do {                                                                                     \
     cudaError_t e__ = (expr);                                                              \
-    if (e__ != cudaSuccess) {                                                              \
-      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
-      (h)->sticky_cuda_error = true;                                                       \
-      return B200CONV_ECUDA;                                                               \
-    }                                                                                      \
+    if (e__ != cudaSuccess) return cuda_fail((h), e__, #expr);                             \
   } while (0)
 
 int fail(b200conv* h, int code, const std::string& msg) { h->err = msg; return code; }
@@ -610,8 +636,8 @@ int clear_state(b200conv* h) {
   return 0;
 }
 
-int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* offsets,
-                const float* const* ir, const size_t* ir_len) {
+int init_impl(b200conv* h, int n_stages, const size_t* blocks, const size_t* offsets,
+              const float* const* ir, const size_t* ir_len) {
   if (int rc = set_device(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   CU_CHECK(h, cudaStreamSynchronize(h->s_post));
@@ -631,8 +657,11 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
   std::vector<Stage> st;
   for (int s = 0; s < n_stages; ++s) {
     Stage x;
-    const size_t b = next_pow2(blocks[s]);                    // FFTConvolver.cpp:113
-    if (b > (size_t(1) << kMaxBlockLog2)) return fail(h, B200CONV_EINVAL, "block size > 8192 not supported");
+    // FFTConvolver.cpp:113 rounds up to a power of two.  Partition sizes above 8192 are clamped to 8192: the
+    // output of a partitioned convolver is the same linear convolution whatever the partition size, and
+    // every offset that is a multiple of a larger power of two is a multiple of 8192 too (REEV-R asks for
+    // tail = max(8192, 2*head), StereoConvolver.cpp:15, i.e. 16384 for host blocks above 4096 samples).
+    const size_t b = std::min(next_pow2(blocks[s]), size_t(1) << kMaxBlockLog2);
     x.B = (int)b;
     x.tap_off = offsets ? offsets[s] : 0;
     x.tap_end = (s + 1 < n_stages) ? offsets[s + 1] : Lir;
@@ -650,8 +679,8 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
   for (auto& x : st) h->Lmax = std::max(h->Lmax, (size_t)2 * x.B);
   h->stages = st;
   for (auto& s : h->stages) {
-    if (int rc = build_stage(h, s, ir, L)) { free_all(h); return rc; }
-    if (int rc = alloc_stage_state(h, s)) { free_all(h); return rc; }
+    if (int rc = build_stage(h, s, ir, L)) return rc;
+    if (int rc = alloc_stage_state(h, s)) return rc;
   }
   for (int i = 0; i < 2; ++i) {
     CU_CHECK(h, cudaMalloc(&h->din[i], (size_t)C * h->Lmax * sizeof(float)));
@@ -662,9 +691,22 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
   h->hpin_cap = std::min(h->Lmax, std::max((size_t)64 * B0, (size_t)16384));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_in, (size_t)C * h->hpin_cap * sizeof(float)));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_out, (size_t)C * h->hpin_cap * sizeof(float)));
-  if (int rc = clear_state(h)) { free_all(h); return rc; }
+  if (int rc = clear_state(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return B200CONV_OK;
+}
+
+// A failed load (e.g. B200CONV_ENOMEM for an IR that does not fit) leaves the handle in the "no IR" state:
+// nothing half-allocated, later init / process calls work.
+int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* offsets,
+                const float* const* ir, const size_t* ir_len) {
+  const int rc = init_impl(h, n_stages, blocks, offsets, ir, ir_len);
+  if (rc != B200CONV_OK && !h->sticky_cuda_error) {
+    const std::string keep = h->err;
+    free_all(h);
+    h->err = keep;
+  }
+  return rc;
 }
 
 // copies `count` samples of every convolver channel from the caller's device buffer (n_in routed inputs or
@@ -781,10 +823,14 @@ int p2p_alloc(b200conv* h) {
 // after a host synchronisation: did a flag barrier give up waiting for a peer?
 int p2p_check(b200conv* h) {
 #if !defined(PC_EMULATE)
-  if (h->p2p_on) {
+  if (h->xflags && h->bar_epoch + h->in_epoch > 0) {
     unsigned int err = 0;
     CU_CHECK(h, cudaMemcpy(&err, h->xflags + 8, sizeof(err), cudaMemcpyDeviceToHost));
-    if (err != 0) return fail(h, B200CONV_ECUDA, "slot-exchange barrier timed out waiting for a peer GPU");
+    if (err != 0) {
+      // report once, then re-arm: one slow peer must not fail every later call
+      CU_CHECK(h, cudaMemset(h->xflags + 8, 0, sizeof(unsigned int)));
+      return fail(h, B200CONV_ECUDA, "slot-exchange barrier timed out waiting for a peer GPU (audio of this call is incomplete)");
+    }
   }
 #else
   (void)h;
@@ -813,6 +859,14 @@ int p2p_barrier(b200conv* h, cudaStream_t st, int bank = 0) {
   bp.my_flags = h->xflags + 16 * bank;
   bp.error_word = h->xflags + 8;
   bp.rank = h->cfg.shard_rank; bp.G = h->cfg.shard_count; bp.epoch = epoch;
+  {
+    static const unsigned long long timeout_ms = [] {
+      const char* e = std::getenv("B200CONV_P2P_TIMEOUT_MS");
+      const long long v = e ? std::atoll(e) : 0;
+      return (unsigned long long)(v > 0 ? v : 20000);      // default 20 s: a peer may be loading modules / paging in
+    }();
+    bp.timeout_ns = timeout_ms * 1000000ull;
+  }
   pc::k_p2p_barrier<<<1, 32, 0, st>>>(bp);
   h->launches++;
   CU_CHECK(h, cudaGetLastError());
@@ -1236,6 +1290,7 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
   // no host memset either: that would cost more than the whole step on the throughput path)
   float* const* out = (out_user && h->cfg.shard_rank != 0) ? nullptr : out_user;
   if (int rc = set_device(h)) return rc;
+  if (h->timing) h->ev_used = 0;
   const int C = h->C;
   const int Cin = h->route_on ? h->n_in : C, Cout = h->route_on ? h->n_out : C;
   if (h->stages.empty()) {
@@ -1336,6 +1391,11 @@ int b200conv_process_xfade(b200conv_t* ho, b200conv_t* hn, const float* const* i
       }
     return B200CONV_OK;
   }
+#if !defined(PC_EMULATE)
+  if (ho->Lmax != hn->Lmax) return fail(hn, B200CONV_EINVAL, "crossfade needs equal staging sizes (same head block and batch size)");
+#endif
+  if (ho->timing) ho->ev_used = 0;
+  if (hn->timing) hn->ev_used = 0;
   const size_t chunk = std::min(ho->Lmax - ho->stages[0].B, hn->Lmax - hn->stages[0].B);
   for (size_t done = 0; done < len;) {
     const size_t n = std::min(len - done, chunk);
@@ -1357,7 +1417,6 @@ int b200conv_process_xfade(b200conv_t* ho, b200conv_t* hn, const float* const* i
         *d = (1.0f - al) * ho->dout[0][(size_t)c * ho->Lmax + i] + al * *d;
       }
 #else
-    if (ho->Lmax != hn->Lmax) return fail(hn, B200CONV_EINVAL, "crossfade needs equal staging sizes (same head block and batch size)");
     dim3 grid((unsigned)((n + 255) / 256), Cout, 1);
     pc::k_xfade<<<grid, 256, 0, hn->s_main>>>(hn->dout[0], ho->dout[0], hn->dout[0], (long long)hn->Lmax, (long long)n, a0, alpha_step);
     hn->launches++;
@@ -1376,7 +1435,7 @@ int b200conv_clear(b200conv_t* h) {
   if (int rc = set_device(h)) return rc;
   if (int rc = clear_state(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
-  return B200CONV_OK;
+  return p2p_check(h);
 }
 
 int b200conv_reset(b200conv_t* h) {
@@ -1447,8 +1506,26 @@ int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, 
 
 size_t b200conv_p2p_blob_size(const b200conv_t* h) { (void)h; return sizeof(P2PRecord) * kP2PBuffers; }
 
+static int p2p_export_impl(b200conv_t* h, void* blob, int mode);
+static int p2p_import_impl(b200conv_t* h, const void* all_blobs);
+
+// A failed export / import (CUDA IPC not permitted in this container, out of memory for the exchange
+// buffers, ...) releases whatever was set up and leaves the handle usable on the reduce-hook path.
 int b200conv_p2p_export(b200conv_t* h, void* blob, int mode) {
   REQUIRE_CUDA(h);
+  const int rc = p2p_export_impl(h, blob, mode);
+  if (rc != B200CONV_OK && rc != B200CONV_EINVAL && !h->sticky_cuda_error) { const std::string keep = h->err; p2p_release(h); h->err = keep; }
+  return rc;
+}
+
+int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
+  REQUIRE_CUDA(h);
+  const int rc = p2p_import_impl(h, all_blobs);
+  if (rc != B200CONV_OK && !h->sticky_cuda_error) { const std::string keep = h->err; p2p_release(h); h->err = keep; }
+  return rc;
+}
+
+static int p2p_export_impl(b200conv_t* h, void* blob, int mode) {
   if (!blob) return fail(h, B200CONV_EINVAL, "null blob");
   if (h->cfg.shard_count < 2 || h->cfg.shard_count > 8) return fail(h, B200CONV_ESTATE, "slot exchange needs 2..8 shards");
   if (h->stages.size() != 1) return fail(h, B200CONV_ESTATE, "slot exchange supports uniform (single-stage) handles");
@@ -1477,8 +1554,7 @@ int b200conv_p2p_export(b200conv_t* h, void* blob, int mode) {
   return B200CONV_OK;
 }
 
-int b200conv_p2p_import(b200conv_t* h, const void* all_blobs) {
-  REQUIRE_CUDA(h);
+static int p2p_import_impl(b200conv_t* h, const void* all_blobs) {
   if (!all_blobs || !h->Yx[0]) return fail(h, B200CONV_ESTATE, "export before import");
   if (int rc = set_device(h)) return rc;
   const int G = h->cfg.shard_count, me = h->cfg.shard_rank;
@@ -1552,9 +1628,10 @@ int b200conv_p2p_set_input_broadcast(b200conv_t* h, int enable) {
 int b200conv_p2p_detach(b200conv_t* h) {
   if (!h) return B200CONV_EINVAL;
   if (h->s_main) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->s_main); if (h->s_post) cudaStreamSynchronize(h->s_post); }
+  const int rc = h->sticky_cuda_error ? B200CONV_OK : p2p_check(h);   // a barrier that gave up is reported here at the latest
   h->p2p_on = false;
   h->bcast_in = false;
-  return B200CONV_OK;
+  return rc;
 }
 
 int b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* user) {
@@ -1562,6 +1639,11 @@ int b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void* u
   h->host_barrier = fn; h->host_barrier_user = user;
   return B200CONV_OK;
 }
+
+#if defined(PC_EMULATE)
+// tests/emu only: make the (n+1)-th device allocation from now fail once
+void pc_emu_fail_malloc_after(int n) { g_emu_fail_malloc_in = n; }
+#endif
 
 void* b200conv_alloc_host(size_t bytes) {
   void* p = nullptr;

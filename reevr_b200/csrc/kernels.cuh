@@ -890,8 +890,8 @@ __global__ void __launch_bounds__(32 * PW) k_cmac_stream(StreamParams P) {
 // ------------------------------------------------------------------------------------------
 // Cross-GPU barrier over peer-mapped flag words (slot exchange).  One CTA, thread t < G:
 // publishes `epoch` in peer t's flag array at index `rank`, then waits until peer t has published
-// the same epoch here.  Flags only grow, so no reset is needed.  A bounded spin turns a lost peer
-// into an error word instead of a hung GPU.
+// the same epoch here.  Flags only grow, so no reset is needed.  A spin bounded in wall-clock time
+// (BarrierParams::timeout_ns) turns a lost peer into an error word instead of a hung GPU.
 // ------------------------------------------------------------------------------------------
 struct BarrierParams {
   unsigned int* peer_flags[8];   // flag array (8 words) of every rank, peer-mapped
@@ -899,6 +899,7 @@ struct BarrierParams {
   unsigned int* error_word;      // set to epoch on timeout
   int rank, G;
   unsigned int epoch;
+  unsigned long long timeout_ns;   // wall-clock bound of the spin (%globaltimer)
 };
 
 static __global__ void k_p2p_barrier(BarrierParams P) {
@@ -909,10 +910,12 @@ static __global__ void k_p2p_barrier(BarrierParams P) {
   *out = P.epoch;
   __threadfence_system();
   volatile unsigned int* in = P.my_flags + t;
-  long long spins = 0;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while ((int)(*in - P.epoch) < 0) {
-    if (++spins > (1LL << 24)) { *P.error_word = P.epoch; break; }
     __nanosleep(64);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > P.timeout_ns) { *P.error_word = P.epoch; break; }
   }
   __threadfence_system();
 }

@@ -35,7 +35,10 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
+// fault injection for the error-path tests: the (n+1)-th cudaMalloc from now fails once (n < 0: off)
+inline int g_emu_fail_malloc_in = -1;
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
+  if (g_emu_fail_malloc_in >= 0 && g_emu_fail_malloc_in-- == 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
   *p = (T*)std::malloc(n ? n : 1);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }

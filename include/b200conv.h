@@ -75,6 +75,24 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
 int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride,
                             float* out_dev, size_t out_stride, size_t len, int sync);
 
+/* Time-slice sharding of an offline / batch call over several GPUs — no collective, no exchange.  Every GPU holds
+ * the WHOLE convolver (a handle with the same IR and the same history, shard_count = 1); for one call of `len`
+ * samples GPU `slice_rank` of `slice_count` produces only the output blocks [a, b) of its contiguous time slice
+ * (ceil(T / slice_count) blocks each) and writes out[c][a*B .. b*B) — the rest of `out` is left untouched for the
+ * other GPUs (which are given the same `in` / `out` arrays, e.g. one shared, pinned host buffer, or run in other
+ * threads of the same process).  The sum over partitions of FFTConvolver.cpp:179-187 needs the spectra of the P
+ * blocks in front of a slice: the GPU uploads and forward-transforms that history (FFT only, no sweep), convolves its
+ * slice, then transforms the last P blocks of the call, so that after the call EVERY handle is in the state the
+ * whole call would have left (the next call — sliced or not — continues the stream).  Per GPU: T/G + P blocks
+ * of H2D and forward FFT, T/G blocks of sweep, inverse FFT and D2H.  Pays off when T/G >> P (batch jobs); for
+ * streaming calls and IRs longer than the batch use the partition-range shards below.
+ * Needs: uniform (single-stage) handle, no routing, no open block, len a multiple of the block size
+ * (else B200CONV_ESTATE, nothing processed). */
+int b200conv_process_sliced(b200conv_t* h, const float* const* in, float* const* out, size_t len,
+                            int slice_rank, int slice_count);
+int b200conv_process_device_sliced(b200conv_t* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride,
+                                   size_t len, int slice_rank, int slice_count, int sync);
+
 /* FFTConvolver::clear (FFTConvolver.cpp:80-90) / TwoStageFFTConvolver::clear (:69-84): forget
  * all audio history, keep the IR.  Implemented as a TRUE clear (also mid-block), see DESIGN.md. */
 int b200conv_clear(b200conv_t* h);
@@ -159,9 +177,12 @@ int    b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void
  * left untouched).  Stand-alone call: no handle, own temporary device buffers. */
 int b200conv_ir_decay_eq(int device, float* ir, size_t n, const double* lut, double srate);
 
-/* Pinned host memory helpers (staging buffers for the e2e path). */
+/* Pinned host memory helpers (staging buffers for the e2e path).  register/unregister page-lock memory the caller
+ * owns (e.g. a shared-memory region several per-GPU processes write their output slices into). */
 void* b200conv_alloc_host(size_t bytes);
 void  b200conv_free_host(void* p);
+int   b200conv_register_host(void* p, size_t bytes);
+int   b200conv_unregister_host(void* p);
 
 /* Version / build info string ("b200conv x.y sm_100a ..."). */
 const char* b200conv_version(void);

@@ -69,6 +69,11 @@ SYMBOLS = [
     ("b200conv_p2p_set_input_broadcast", C.c_int, [C.c_void_p, C.c_int]),
     ("b200conv_p2p_set_host_barrier", C.c_int, [C.c_void_p, BARRIER_FN, C.c_void_p]),
     ("b200conv_ir_decay_eq", C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]),
+    ("b200conv_process_sliced", C.c_int, [C.c_void_p, _PP, _PP, C.c_size_t, C.c_int, C.c_int]),
+    ("b200conv_process_device_sliced", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                  C.c_int, C.c_int, C.c_int]),
+    ("b200conv_register_host", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("b200conv_unregister_host", C.c_int, [C.c_void_p]),
     ("b200conv_alloc_host", C.c_void_p, [C.c_size_t]),
     ("b200conv_free_host", None, [C.c_void_p]),
     ("b200conv_version", C.c_char_p, []),

@@ -112,6 +112,21 @@ class Engine:
         self._check(self._l.b200conv_process_device(self._h, in_ptr, in_stride, out_ptr, out_stride, n, int(sync)),
                     "process_device")
 
+    def process_sliced(self, xs, ys, slice_rank: int, slice_count: int) -> None:
+        """Time-slice sharding (b200conv_process_sliced): xs / ys are the WHOLE call's host arrays; only this
+        rank's slice of every ys[c] is written."""
+        n = xs[0].size
+        self._check(self._l.b200conv_process_sliced(self._h, _ptr_array(xs), _ptr_array(ys), n, slice_rank, slice_count),
+                    "process_sliced")
+
+    def process_sliced_into(self, in_ptrs, out_ptrs, n: int, slice_rank: int, slice_count: int) -> None:
+        self._check(self._l.b200conv_process_sliced(self._h, in_ptrs, out_ptrs, n, slice_rank, slice_count), "process_sliced")
+
+    def process_device_sliced(self, in_ptr: int, in_stride: int, out_ptr: int, out_stride: int, n: int,
+                              slice_rank: int, slice_count: int, sync: bool = False):
+        self._check(self._l.b200conv_process_device_sliced(self._h, in_ptr, in_stride, out_ptr, out_stride, n,
+                                                           slice_rank, slice_count, int(sync)), "process_device_sliced")
+
     def clear(self):
         self._check(self._l.b200conv_clear(self._h), "clear")
 

@@ -116,6 +116,9 @@ struct b200conv {
   int in_map[8] = {};
   float mix[64] = {};
   float* dch[1] = {nullptr};                // per-convolver outputs [C][Lmax] before the mixdown
+  // time-slice sharding: Y row 0 (the overlap state, spectrum of the last completed block) does not belong to
+  // the block in front of the open one any more (the timeline was advanced by forward FFTs only)
+  bool yprev_stale = false;
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -626,6 +629,7 @@ int clear_state(b200conv* h) {
     s.fill = 0;
   }
   h->abs_pos = 0;
+  h->yprev_stale = false;
   if (h->Yx[0]) {
     const Stage& s0 = h->stages[0];
     const size_t row = (size_t)h->C * s0.B;
@@ -1018,6 +1022,22 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
 
       // Y[yb] rows >= 1 may still be read by the post work of two groups ago
       if (overlap) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb], 0));
+      if (si == 0 && h->yprev_stale) {
+        // overlap state after a forward-FFT-only advance (time-slice sharding): Y row 0 := sum_p H[p] X[head-1-p],
+        // the spectrum of the block in front of this group, from the timeline (one-block streaming sweep)
+        if (overlap) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb ^ 1], 0));   // row 0 was written on s_post
+        pc::CmacParams c0{};
+        c0.H = s.H; c0.h_cstride = (long long)s.Prows * B;
+        c0.X = s.X; c0.x_cstride = (long long)s.R * B; c0.xrow0 = s.head - 1 - s.p_begin;
+        c0.Y = Yb; c0.y_cstride = B; c0.y_rstride = (long long)row; c0.yrow0 = 0;
+        c0.B = B; c0.Ppad = s.P; c0.nblocks = 1;
+        const bool tm = h->timing; h->timing = false;       // not a launch of the dominant (batched) sweep
+        const int variant = h->cfg.cmac_variant; h->cfg.cmac_variant = 0;
+        const int rc0 = launch_cmac(h, c0, C);
+        h->timing = tm; h->cfg.cmac_variant = variant;
+        if (rc0) return rc0;
+        h->yprev_stale = false;
+      }
       pc::CmacParams cp{};
       cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
       cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
@@ -1085,6 +1105,55 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
     s.fill = partial;
   }
   h->abs_pos += (long long)n;
+  return 0;
+}
+
+// Forward FFTs only (uniform handle, no open block): the spectra of `nblocks` input blocks go into the timeline,
+// no sweep, no output.  Used by the time-slice sharding for the history in front of a slice and for the tail of
+// the call every GPU keeps.
+int advance_fft_only(b200conv* h, const float* in_dev, size_t in_stride, long long nblocks) {
+  Stage& s = h->stages[0];
+  const int C = h->C, B = s.B;
+  for (long long done = 0; done < nblocks;) {
+    const int nb = (int)std::min<long long>(nblocks - done, s.Tcap);
+    if (s.head + nb + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
+    pc::FwdParams fp{};
+    fp.src = in_dev + (size_t)done * B; fp.src_cstride = (long long)in_stride;
+    fp.nvalid_c = nullptr; fp.nvalid = (long long)nb * B;
+    set_cmap(h, fp, false);
+    fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
+    fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+    if (int rc = launch_fwd(h, fp, C)) return rc;
+    s.head += nb;
+    s.blocks_done += nb;
+    done += nb;
+  }
+  if (nblocks > 0) h->yprev_stale = true;
+  h->abs_pos += nblocks * B;
+  return 0;
+}
+
+// Time-slice sharding of one block-aligned call of T blocks (see b200conv_process_sliced): which blocks this
+// GPU transforms only ([lo, a) in front of its slice, [tail_lo, T) behind it) and which it convolves ([a, b)).
+struct SlicePlan { long long T, a, b, lo, tail_lo; };
+
+int plan_slice(b200conv* h, size_t len, int rank, int count, SlicePlan* sp) {
+  if (count < 1 || rank < 0 || rank >= count) return fail(h, B200CONV_EINVAL, "slice_rank / slice_count out of range");
+  if (h->stages.size() != 1) return fail(h, B200CONV_ESTATE, "time-slice sharding needs a uniform (single-stage) handle");
+  if (h->cfg.shard_count != 1) return fail(h, B200CONV_ESTATE, "time-slice sharding needs an unsharded handle (the full IR on every GPU)");
+  if (h->route_on) return fail(h, B200CONV_ESTATE, "time-slice sharding is not available with I/O routing");
+  const Stage& s = h->stages[0];
+  if (s.fill != 0 || len % (size_t)s.B != 0)
+    return fail(h, B200CONV_ESTATE, "time-slice sharding needs block-aligned calls (len a multiple of the block size, no open block)");
+  const long long T = (long long)(len / (size_t)s.B), P = s.P_full;
+  const long long per = (T + count - 1) / count;
+  sp->T = T;
+  sp->a = std::min(T, rank * per);
+  sp->b = std::min(T, (rank + 1) * per);
+  // block t needs X[t-p], p < P, and the overlap-add needs the spectrum of block t-1 as well: P blocks of history
+  sp->lo = sp->b > sp->a ? std::max(0LL, sp->a - P) : sp->a;
+  sp->tail_lo = std::max(sp->b, T - P);
+  if (sp->b <= sp->a) { sp->a = sp->b = sp->lo = std::max(0LL, T - P); sp->tail_lo = sp->a; }   // empty slice: only keep the tail
   return 0;
 }
 
@@ -1367,6 +1436,128 @@ int b200conv_process(b200conv_t* h, const float* const* in, float* const* out, s
 }
 
 int b200conv_prime(b200conv_t* h, const float* const* in, size_t len) { return process_impl(h, in, nullptr, len); }
+
+int b200conv_process_device_sliced(b200conv_t* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride,
+                                   size_t len, int slice_rank, int slice_count, int sync) {
+  REQUIRE_CUDA(h);
+  if (int rc = set_device(h)) return rc;
+  if (h->timing) h->ev_used = 0;
+  if (h->stages.empty()) {
+    if (len) CU_CHECK(h, cudaMemset2DAsync(out_dev, out_stride * sizeof(float), 0, len * sizeof(float), h->C, h->s_main));
+  } else {
+    SlicePlan sp;
+    if (int rc = plan_slice(h, len, slice_rank, slice_count, &sp)) return rc;
+    Stage& s = h->stages[0];
+    const size_t B = (size_t)s.B;
+    const long long done0 = s.blocks_done, pos0 = h->abs_pos;
+    if (int rc = advance_fft_only(h, in_dev + (size_t)sp.lo * B, in_stride, sp.a - sp.lo)) return rc;
+    const size_t chunk = (h->Lmax - B) / B * B;
+    const size_t n_slice = (size_t)(sp.b - sp.a) * B;
+    const bool overlap = n_slice > chunk;
+    for (size_t done = 0; done < n_slice;) {
+      const size_t n = std::min(n_slice - done, chunk);
+      const size_t off = (size_t)sp.a * B + done;
+      if (int rc = run_group(h, in_dev + off, in_stride, out_dev + off, out_stride, n, overlap)) return rc;
+      done += n;
+    }
+    if (overlap) { if (int rc = join_post(h)) return rc; }
+    if (int rc = advance_fft_only(h, in_dev + (size_t)sp.tail_lo * B, in_stride, sp.T - sp.tail_lo)) return rc;
+    s.blocks_done = done0 + sp.T;               // the state is that of the whole call
+    h->abs_pos = pos0 + (long long)len;
+  }
+  if (sync || h->timing) {
+    CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    if (h->timing) timing_collect(h);
+  }
+  return B200CONV_OK;
+}
+
+int b200conv_process_sliced(b200conv_t* h, const float* const* in, float* const* out, size_t len, int slice_rank, int slice_count) {
+  REQUIRE_CUDA(h);
+  if (len == 0) return B200CONV_OK;
+  if (!in || !out) return fail(h, B200CONV_EINVAL, "null buffer");
+  if (int rc = set_device(h)) return rc;
+  if (h->timing) h->ev_used = 0;
+  const int C = h->C;
+  if (h->stages.empty()) {                      // no IR: zeros (FFTConvolver.cpp:157-161); every GPU writes the same value
+    for (int c = 0; c < C; ++c) std::memset(out[c], 0, len * sizeof(float));
+    return B200CONV_OK;
+  }
+  SlicePlan sp;
+  if (int rc = plan_slice(h, len, slice_rank, slice_count, &sp)) return rc;
+  Stage& s = h->stages[0];
+  const size_t B = (size_t)s.B;
+  const long long done0 = s.blocks_done, pos0 = h->abs_pos;
+  // pieces of at most `grp` samples, each one H2D -> (forward FFTs | full group) -> D2H, pipelined over the three
+  // streams like b200conv_process: [lo, a) and [tail_lo, T) are transformed only, [a, b) is convolved
+  const size_t chunk = (h->Lmax - B) / B * B;
+  const size_t tile = B * 64;
+  const size_t cols = (size_t)((B + 31) / 32) * (size_t)C;
+  size_t wave = ((size_t)h->n_sm * 3 * 64 + cols - 1) / cols * B;
+  wave = std::max(tile, wave / tile * tile);
+  const size_t n_slice = (size_t)(sp.b - sp.a) * B;
+  size_t grp = std::max(wave, (n_slice / 4) / wave * wave);
+  grp = std::min(grp, chunk >= tile ? chunk / tile * tile : chunk);
+  struct Piece { size_t off, n; bool conv; };
+  std::vector<Piece> pieces;
+  auto add = [&](long long b0, long long b1, bool conv) {
+    for (size_t o = (size_t)b0 * B, e = (size_t)b1 * B; o < e; o += grp) pieces.push_back({o, std::min(grp, e - o), conv});
+  };
+  add(sp.lo, sp.a, false);
+  add(sp.a, sp.b, true);
+  add(sp.tail_lo, sp.T, false);
+  int i = 0;
+  bool used_out[2] = {false, false};
+  for (const Piece& pc_ : pieces) {
+    const int b = i & 1;
+    if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_din[b], 0));
+    for (int c = 0; c < C; ++c)
+      CU_CHECK(h, cudaMemcpyAsync(h->din[b] + (size_t)c * h->Lmax, in[c] + pc_.off, pc_.n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+    CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
+    CU_CHECK(h, cudaStreamWaitEvent(h->s_main, h->ev_h2d[b], 0));
+    if (!pc_.conv) {
+      if (int rc = advance_fft_only(h, h->din[b], h->Lmax, (long long)(pc_.n / B))) return rc;
+      CU_CHECK(h, cudaEventRecord(h->ev_din[b], h->s_main));
+    } else {
+      if (used_out[b]) CU_CHECK(h, cudaStreamWaitEvent(h->s_post, h->ev_d2h[b], 0));
+      if (int rc = run_group(h, h->din[b], h->Lmax, h->dout[b], h->Lmax, pc_.n, true)) return rc;
+      CU_CHECK(h, cudaEventRecord(h->ev_din[b], h->s_main));
+      CU_CHECK(h, cudaEventRecord(h->ev_comp[b], h->s_post));
+      CU_CHECK(h, cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+      for (int c = 0; c < C; ++c)
+        CU_CHECK(h, cudaMemcpyAsync(out[c] + pc_.off, h->dout[b] + (size_t)c * h->Lmax, pc_.n * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      CU_CHECK(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
+      used_out[b] = true;
+    }
+    ++i;
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->s_out));
+  if (int rc = join_post(h)) return rc;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  s.blocks_done = done0 + sp.T;
+  h->abs_pos = pos0 + (long long)len;
+  return B200CONV_OK;
+}
+
+int b200conv_register_host(void* p, size_t bytes) {
+#if defined(PC_EMULATE)
+  (void)p; (void)bytes;
+  return B200CONV_OK;
+#else
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return B200CONV_ECUDA; }
+  return B200CONV_OK;
+#endif
+}
+
+int b200conv_unregister_host(void* p) {
+#if defined(PC_EMULATE)
+  (void)p;
+  return B200CONV_OK;
+#else
+  if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return B200CONV_ECUDA; }
+  return B200CONV_OK;
+#endif
+}
 
 int b200conv_process_xfade(b200conv_t* ho, b200conv_t* hn, const float* const* in, float* const* out,
                            size_t len, float alpha0, float alpha_step) {

@@ -38,6 +38,7 @@
 
 #include "../../include/b200conv.h"
 #include "kernels.cuh"
+#include "kernels_stream.cuh"
 
 namespace {
 
@@ -301,6 +302,14 @@ bool fft_set_smem_attr() {
   ok = ok && cudaFuncSetAttribute(pc::k_inv_fft_ola<(1 << L), false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) == cudaSuccess;
   return ok;
 }
+bool stream_set_smem_attr() {
+  bool ok = true;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * pc::kStreamStageBytes + 64) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * pc::kStreamStageBytes + 64) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * pc::kStreamStageBytes + 128) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * pc::kStreamStageBytes + 256) == cudaSuccess;
+  return ok;
+}
 #define PC_FOR_EACH_LOG2(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 #endif
 
@@ -456,6 +465,47 @@ int launch_cmac_stream_rows(b200conv* h, const pc::CmacParams& P, int C) {
   return 0;
 }
 
+// TMA-fed streaming sweep (one block per launch, B >= 64): see kernels_stream.cuh.  S ring stages of 16 KB per
+// CTA, `per_sm` CTAs per SM (S * per_sm * 16 KB <= 192 KB of shared memory per SM in flight).
+template <int S>
+int launch_stream_tma_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
+#if defined(PC_EMULATE)
+  pc::emu_cmac_stream_tma({(int)grid.x, (int)grid.y, (int)grid.z}, S_);
+#else
+  const size_t smem = (size_t)S * pc::kStreamStageBytes + 16 * S;
+  pc::k_cmac_stream_tma<S><<<grid, dim3(288, 1, 1), smem, h->s_main>>>(S_);
+#endif
+  return 0;
+}
+
+int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stages, int per_sm) {
+  pc::StreamParams S{};
+  S.H = P.H; S.h_cstride = P.h_cstride;
+  S.X = P.X; S.x_cstride = P.x_cstride; S.xrow0 = P.xrow0;
+  S.Y = P.Y; S.y_cstride = P.y_cstride; S.y_rstride = P.y_rstride; S.yrow0 = P.yrow0;
+  S.B = P.B; S.P = P.Ppad; S.nblocks = 1;
+  const int W = pc::stream_tma_w(P.B), PP = pc::stream_tma_pp(P.B), RG = pc::stream_tma_rg(P.B);
+  const int xt = P.B / W;
+  // per_sm CTAs per SM, but no CTA with fewer than two ring stages of partitions
+  int nsplit = std::max(1, (per_sm * h->n_sm) / std::max(1, xt * C));
+  nsplit = std::max(1, std::min(nsplit, std::max(1, P.Ppad / (2 * PP))));
+  S.nsplit = nsplit;
+  if (nsplit > 1 || RG > 1)
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_main));
+  dim3 grid(xt, nsplit, C);
+  int id = timing_begin(h, kKindCmac);
+  switch (stages) {
+    case 2: launch_stream_tma_s<2>(h, S, grid); break;
+    case 6: launch_stream_tma_s<6>(h, S, grid); break;
+    case 12: launch_stream_tma_s<12>(h, S, grid); break;
+    default: launch_stream_tma_s<4>(h, S, grid); break;
+  }
+  timing_end(h, id);
+  h->launches++;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+}
+
 // P.Ppad enters as the number of real (unpadded) partition rows of this shard
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
@@ -463,9 +513,16 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   if (variant == 0) {
     // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
     // launch group is long enough to fill 16-block tiles, TT = 8 below that)
-    if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
+    if (P.nblocks == 1 && P.B >= 64 && P.Ppad >= 1) variant = 102;
+    else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;
+  }
+  if (variant >= 102 && variant <= 105) {
+    if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");
+    // 102: 4 stages x 3 CTAs/SM   103: 6 x 2   104: 12 x 1   105: 2 x 6    (all 192 KB in flight per SM)
+    static const int cfg[4][2] = {{4, 3}, {6, 2}, {12, 1}, {2, 6}};
+    return launch_cmac_stream_tma(h, P, C, cfg[variant - 102][0], cfg[variant - 102][1]);
   }
   if (variant == 101) {
     if (P.nblocks > kStreamNBS || P.B < 4) return fail(h, B200CONV_EINVAL, "streaming sweep needs nblocks <= 4 and B >= 4");
@@ -1223,6 +1280,7 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
 #define PC_CASE(L) attr_ok = attr_ok && fft_set_smem_attr<L>();
       PC_FOR_EACH_LOG2(PC_CASE)
 #undef PC_CASE
+      attr_ok = attr_ok && stream_set_smem_attr();
     });
     ok = attr_ok;
   }

@@ -256,6 +256,31 @@ def test_cmac_variants(lib, variant):
     assert peak_err(y, o.run(x, 64)) <= TOL
 
 
+@pytest.mark.parametrize("variant", [100, 101, 102, 103, 104, 105])
+@pytest.mark.parametrize("B,nparts", [(64, 37), (128, 9), (512, 21), (1024, 5), (2048, 3)])
+def test_streaming_sweep_variants(lib, variant, B, nparts):
+    """One block per launch (the real-time call): register-batch and TMA-ring forms of the streaming sweep, block
+    sizes on both sides of the 512-bin CTA tile, partition counts that leave ragged ring stages, 2 channels."""
+    if variant == 100 and B > 512:
+        pytest.skip("generic fallback kernel is only selected below 64 bins")
+    irs = [orc.synth_ir(nparts * B - 3, c) for c in range(2)]
+    x = [orc.synth_input(B * 12 + 40, c) for c in range(2)]
+    e = Engine(2, cmac_variant=variant, lib=lib)
+    assert e.init_uniform(B, irs)
+    chunks = [B] * 6 + [40, B - 40] + [B] * 5            # whole blocks, one block in two calls
+    ys = [[], []]
+    pos = 0
+    for k in chunks:
+        out = e.process([a[pos:pos + k] for a in x])
+        for c in range(2):
+            ys[c].append(out[c])
+        pos += k
+    for c in range(2):
+        o = orc.OracleUniform()
+        o.init(B, irs[c])
+        assert peak_err(np.concatenate(ys[c]), o.process(x[c][:pos])) <= TOL
+
+
 def test_device_mixdown_quad(lib):
     """StereoConvolver quad as ONE call with 2 inputs / 2 outputs and the true-stereo
     mixdown on the device (src/PluginProcessor.cpp:1833-1838: wet L = LL + RL, wet R = RR + LR)."""

@@ -513,7 +513,7 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   if (variant == 0) {
     // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
     // launch group is long enough to fill 16-block tiles, TT = 8 below that)
-    if (P.nblocks == 1 && P.B >= 64 && P.Ppad >= 1) variant = 102;
+    if (P.nblocks == 1 && P.B >= 64 && P.Ppad >= 1) variant = 103;     // TMA ring, 6 stages x 2 CTAs/SM (best on the 120 s IR)
     else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;

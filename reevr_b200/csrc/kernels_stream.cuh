@@ -12,8 +12,9 @@
 // ever touch shared memory:
 //
 //   CTA tile      W = min(B, 512) bins x a contiguous slice of the partition range
-//   stage         PP partitions: PP H-row segments + PP FDL-row segments of W*8 bytes each (2*PP bulk copies,
-//                 16 KB per stage for every B), completion counted in bytes on the stage's `full` mbarrier
+//   stage         PP partitions: PP H-row segments + PP FDL-row segments of W*8 bytes each, 16 KB per stage for
+//                 every B — two 8 KB bulk copies when a tile spans whole rows (B <= 512: consecutive rows are
+//                 contiguous), 2*PP copies of 4 KB otherwise; completion counted in bytes on the stage's `full` mbarrier
 //   ring          S stages (S*16 KB in flight per CTA, up to 3 CTAs per SM = 192 KB per SM), `empty` mbarriers
 //                 (one arrival per consumer warp) hand a stage back to the producer
 //   consumers     thread = one bin pair (16 B) x one partition group; RG = 512 / W partition groups per stage
@@ -48,13 +49,15 @@ PC_HD const float2* stream_src_x(const StreamParams& P, int c, int k0, int p) {
   return P.X + (long long)c * P.x_cstride + (P.xrow0 - p) * (long long)P.B + k0;
 }
 
-// one consumer thread, one stage: stage memory = [PP][W] H segments followed by [PP][W] FDL segments
+// one consumer thread, one stage: stage memory = [PP][W] H segments followed by [PP][W] FDL segments.
+// xrev: the FDL segments were fetched as ONE contiguous run of rows (W == B), i.e. in ascending row = descending
+// partition order, so partition j of the stage sits at segment np-1-j.
 PC_HD void stream_consume_stage(const float2* stage, int W, int PP, int np, int col, int rg, int RG, bool packed_first,
-                                float2* acc /*[2]*/) {
+                                bool xrev, float2* acc /*[2]*/) {
   const float m = packed_first ? 0.0f : 1.0f;
   for (int j = rg; j < np; j += RG) {
     const float2* hp = stage + (long long)j * W + 2 * col;
-    const float2* xp = stage + (long long)(PP + j) * W + 2 * col;
+    const float2* xp = stage + (long long)(PP + (xrev ? np - 1 - j : j)) * W + 2 * col;
     const float2 ha = hp[0], hb = hp[1], xa = xp[0], xb = xp[1];
     float re = fmaf(ha.x, xa.x, acc[0].x);
     re = fmaf(-m * ha.y, xa.y, re);
@@ -119,9 +122,14 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
         const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
         mbar_expect_tx(&full[s], (unsigned)(np * 2 * W * 8));
         float2* st = ring + (size_t)s * kStageElems;
-        for (int j = 0; j < np; ++j) {
-          bulk_g2s(st + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
-          bulk_g2s(st + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
+        if (W == P.B) {          // whole rows: the np rows of H (and of the FDL) are one contiguous run -> 2 copies per stage
+          bulk_g2s(st, stream_src_h(P, c, k0, p0), (unsigned)(np * W * 8), &full[s]);
+          bulk_g2s(st + (size_t)PP * W, stream_src_x(P, c, k0, p0 + np - 1), (unsigned)(np * W * 8), &full[s]);
+        } else {
+          for (int j = 0; j < np; ++j) {
+            bulk_g2s(st + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
+            bulk_g2s(st + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
+          }
         }
       }
     }
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
     const int p0 = p_lo + i * PP;
     const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
     mbar_wait(&full[s], (i / S) & 1);                        // the stage's bytes have landed
-    stream_consume_stage(ring + (size_t)s * kStageElems, W, PP, np, col, rg, RG, packed_first, acc);
+    stream_consume_stage(ring + (size_t)s * kStageElems, W, PP, np, col, rg, RG, packed_first, W == P.B, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
@@ -166,13 +174,18 @@ inline void emu_cmac_stream_tma(EmuDim grid, const StreamParams& P) {
         for (int i = 0; i < nst; ++i) {
           const int p0 = p_lo + i * PP;
           const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
-          for (int j = 0; j < np; ++j) {
-            std::memcpy(stage + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (size_t)W * 8);
-            std::memcpy(stage + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (size_t)W * 8);
+          if (W == P.B) {
+            std::memcpy(stage, stream_src_h(P, c, k0, p0), (size_t)np * W * 8);
+            std::memcpy(stage + (size_t)PP * W, stream_src_x(P, c, k0, p0 + np - 1), (size_t)np * W * 8);
+          } else {
+            for (int j = 0; j < np; ++j) {
+              std::memcpy(stage + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (size_t)W * 8);
+              std::memcpy(stage + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (size_t)W * 8);
+            }
           }
           for (int tid = 0; tid < 256; ++tid) {
             const int col = tid % (W / 2), rg = tid / (W / 2);
-            stream_consume_stage(stage, W, PP, np, col, rg, RG, (k0 + 2 * col) == 0, accs + 2 * tid);
+            stream_consume_stage(stage, W, PP, np, col, rg, RG, (k0 + 2 * col) == 0, W == P.B, accs + 2 * tid);
           }
         }
         for (int tid = 0; tid < 256; ++tid) {

@@ -39,6 +39,7 @@
 #include "../../include/b200conv.h"
 #include "kernels.cuh"
 #include "kernels_stream.cuh"
+#include "kernels_fft512.cuh"
 
 namespace {
 
@@ -73,6 +74,7 @@ struct Stage {
   cudaEvent_t ev_sweep[2] = {nullptr, nullptr};   // Y[b] rows written by the sweep
   cudaEvent_t ev_post[2] = {nullptr, nullptr};    // Y[b] no longer needed by reduce / inverse FFT
   float2* tw = nullptr;
+  float2* tab512 = nullptr;   // B == 512: tables of the register-resident FFT kernels
   float* inbuf = nullptr;
   size_t in_stride = 0;
   float* fut = nullptr;
@@ -186,7 +188,7 @@ int cuda_fail(b200conv* h, cudaError_t e, const char* what) {
 int fail(b200conv* h, int code, const std::string& msg) { h->err = msg; return code; }
 
 void free_stage(Stage& s) {
-  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y[0]); cudaFree(s.Y[1]); cudaFree(s.tw); cudaFree(s.inbuf); cudaFree(s.fut);
+  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y[0]); cudaFree(s.Y[1]); cudaFree(s.tw); cudaFree(s.tab512); cudaFree(s.inbuf); cudaFree(s.fut);
   for (int i = 0; i < 2; ++i) {
     if (s.ev_sweep[i]) cudaEventDestroy(s.ev_sweep[i]);
     if (s.ev_post[i]) cudaEventDestroy(s.ev_post[i]);
@@ -313,7 +315,31 @@ bool stream_set_smem_attr() {
 #define PC_FOR_EACH_LOG2(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 #endif
 
+// register-resident kernels for B = 512 (kernels_fft512.cuh): batches only — a real-time call of a few transforms
+// would pay the per-CTA table staging for nothing
+constexpr int kF512MinTransforms = 32;
+constexpr size_t kF512Smem = (size_t)(pc::kF512_TabLen + 8 * pc::kF512_Xch) * sizeof(float2);
+
+bool use_fft512(const b200conv* h, int M, int nblocks, int C, const float2* tab) {
+  (void)h;
+  static const bool off = std::getenv("B200CONV_NO_FFT512") != nullptr;      // A/B switch for tuning runs
+  return !off && M == pc::kF512_M && tab != nullptr && (long long)nblocks * C >= kF512MinTransforms;
+}
+
 int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
+  if (use_fft512(h, P.M, P.nblocks, C, P.tab512)) {
+    int id = timing_begin(h, kKindFft);
+#if defined(PC_EMULATE)
+    pc::emu_fwd_fft512(P.nblocks, C, P, P.tab512);
+#else
+    const int gx = std::max(1, std::min((P.nblocks + 7) / 8, (4 * h->n_sm + C - 1) / C));
+    pc::k_fwd_fft512<<<dim3(gx, C, 1), dim3(32, 8, 1), kF512Smem, h->s_main>>>(P, P.tab512);
+#endif
+    timing_end(h, id);
+    h->launches++;
+    CU_CHECK(h, cudaGetLastError());
+    return 0;
+  }
   const FftGeom g = fft_geometry(P.M, P.nblocks, C);
   int id = timing_begin(h, kKindFft);
 #if defined(PC_EMULATE)
@@ -333,6 +359,23 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
 }
 
 int launch_inv(b200conv* h, const pc::InvParams& P, int C, cudaStream_t st) {
+  if (P.n_partials <= 1 && use_fft512(h, P.M, P.nblocks, C, P.tab512)) {
+    // whole blocks inside the destination, nothing added on top, linear and 8-byte aligned: float2 stores
+    const bool fast = P.n_add == 0 && P.mask == -1 && P.lo <= P.index0 && P.hi >= P.index0 + (long long)P.nblocks * P.M &&
+                      (P.index0 & 1) == 0 && (P.dst_cstride & 1) == 0 && (reinterpret_cast<size_t>(P.dst) & 7) == 0;
+    int id = timing_begin(h, kKindIfft, st);
+#if defined(PC_EMULATE)
+    pc::emu_inv_fft512(P.nblocks, C, P, P.tab512, fast);
+#else
+    const int gx = std::max(1, std::min((P.nblocks + 7) / 8, (3 * h->n_sm + C - 1) / C));
+    if (fast) pc::k_inv_fft512<true><<<dim3(gx, C, 1), dim3(32, 8, 1), kF512Smem, st>>>(P, P.tab512);
+    else pc::k_inv_fft512<false><<<dim3(gx, C, 1), dim3(32, 8, 1), kF512Smem, st>>>(P, P.tab512);
+#endif
+    timing_end(h, id, st);
+    h->launches++;
+    CU_CHECK(h, cudaGetLastError());
+    return 0;
+  }
   const FftGeom g = fft_geometry(P.M, P.nblocks, C);
   int id = timing_begin(h, kKindIfft, st);
 #if defined(PC_EMULATE)
@@ -617,6 +660,21 @@ int build_stage(b200conv* h, Stage& s, const float* const* ir, const std::vector
   }
   CU_CHECK(h, cudaMalloc(&s.tw, N * sizeof(float2)));
   CU_CHECK(h, cudaMemcpyAsync(s.tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice, h->s_main));
+  std::vector<float2> t512;
+  if (B == pc::kF512_M) {       // tables of kernels_fft512.cuh, in double
+    t512.resize(pc::kF512_TabLen);
+    auto w = [](double num, double den) {
+      const double a = -2.0 * M_PI * num / den;
+      return make_float2((float)std::cos(a), (float)std::sin(a));
+    };
+    for (int k2 = 0; k2 < 8; ++k2)
+      for (int m = 0; m < 64; ++m) t512[pc::kF512_T1 + k2 * 64 + m] = w((double)m * k2, 512.0);
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b) t512[pc::kF512_T2 + a * 8 + b] = w((double)a * b, 64.0);
+    for (int k = 0; k < 512; ++k) t512[pc::kF512_TS + k] = w((double)k, 1024.0);
+    CU_CHECK(h, cudaMalloc(&s.tab512, t512.size() * sizeof(float2)));
+    CU_CHECK(h, cudaMemcpyAsync(s.tab512, t512.data(), t512.size() * sizeof(float2), cudaMemcpyHostToDevice, h->s_main));
+  }
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
 
   // H: upload this shard's taps, transform
@@ -643,7 +701,7 @@ int build_stage(b200conv* h, Stage& s, const float* const* ir, const std::vector
     fp.src = dtaps; fp.src_cstride = (long long)taps_per_c;
     fp.nvalid_c = dnv; fp.nvalid = 0;
     fp.dst = s.H; fp.dst_cstride = (long long)s.Prows * B; fp.dst_row0 = 0;
-    fp.tw = s.tw; fp.M = B; fp.nblocks = s.P;
+    fp.tw = s.tw; fp.tab512 = s.tab512; fp.M = B; fp.nblocks = s.P;
     int rc = launch_fwd(h, fp, C);
     if (rc) { cudaFree(dtaps); cudaFree(dnv); return rc; }
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
@@ -975,7 +1033,7 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
   fp.src_cstride = direct ? (long long)in_stride : (long long)s.in_stride;
   fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
   fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
-  fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+  fp.tw = s.tw; fp.tab512 = s.tab512; fp.M = B; fp.nblocks = nb;
   if (int rc = launch_fwd(h, fp, C)) return rc;
 
   // the exchange buffers of parity yb are free once every GPU finished the inverse FFT of two groups ago
@@ -1005,7 +1063,7 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
     }
     pc::InvParams ip{};
     ip.Y = h->Yx[yb]; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
-    ip.tw = s.tw; ip.M = B; ip.nblocks = j1 - j0; ip.scale = 1.0f / (float)B;
+    ip.tw = s.tw; ip.tab512 = s.tab512; ip.M = B; ip.nblocks = j1 - j0; ip.scale = 1.0f / (float)B;
     ip.n_partials = G; ip.partial_stride = (long long)h->xslot;
     ip.dst = h->peer_xout0[yb]; ip.dst_cstride = (long long)h->Lmax;
     ip.index0 = -(long long)s.fill + (long long)j0 * B; ip.lo = 0; ip.hi = (long long)n; ip.mask = -1;
@@ -1074,7 +1132,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
       fp.nvalid_c = nullptr; fp.nvalid = (long long)total;
       set_cmap(h, fp, direct);
       fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
-      fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+      fp.tw = s.tw; fp.tab512 = s.tab512; fp.M = B; fp.nblocks = nb;
       if (int rc = launch_fwd(h, fp, C)) return rc;
 
       // Y[yb] rows >= 1 may still be read by the post work of two groups ago
@@ -1114,7 +1172,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
       if (root) {
         pc::InvParams ip{};
         ip.Y = Yb; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
-        ip.tw = s.tw; ip.M = B; ip.nblocks = nb; ip.scale = 1.0f / (float)B;
+        ip.tw = s.tw; ip.tab512 = s.tab512; ip.M = B; ip.nblocks = nb; ip.scale = 1.0f / (float)B;
         if (si == 0) {
           ip.dst = h->route_on ? h->dch[0] : out_dev;
           ip.dst_cstride = h->route_on ? (long long)h->Lmax : (long long)out_stride;
@@ -1179,7 +1237,7 @@ int advance_fft_only(b200conv* h, const float* in_dev, size_t in_stride, long lo
     fp.nvalid_c = nullptr; fp.nvalid = (long long)nb * B;
     set_cmap(h, fp, false);
     fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
-    fp.tw = s.tw; fp.M = B; fp.nblocks = nb;
+    fp.tw = s.tw; fp.tab512 = s.tab512; fp.M = B; fp.nblocks = nb;
     if (int rc = launch_fwd(h, fp, C)) return rc;
     s.head += nb;
     s.blocks_done += nb;
@@ -1281,6 +1339,9 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
       PC_FOR_EACH_LOG2(PC_CASE)
 #undef PC_CASE
       attr_ok = attr_ok && stream_set_smem_attr();
+      attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_fwd_fft512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
+      attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_inv_fft512<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
+      attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_inv_fft512<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
     });
     ok = attr_ok;
   }

@@ -545,6 +545,7 @@ struct FwdParams {
   int nblocks;
   int use_cmap;              // routing: channel c reads source channel cmap[c] (StereoConvolver: LL,RR,LR,RL <- L,R,L,R)
   int cmap[8];
+  const float2* tab512;      // tables of the register-resident B = 512 kernels (kernels_fft512.cuh), else nullptr
 };
 
 struct CmacParams {
@@ -605,6 +606,7 @@ struct InvParams {
   int n_add;
   const float* add[3]; long long add_cstride[3]; long long add_mask[3];
   long long abs0;            // absolute stream position of sample 0 of block 0
+  const float2* tab512;      // tables of the register-resident B = 512 kernels (kernels_fft512.cuh), else nullptr
 };
 
 struct StreamParams {

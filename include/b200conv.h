@@ -112,6 +112,9 @@ int    b200conv_stage(const b200conv_t* h, int s, b200conv_stage_info* out);
 size_t b200conv_ir_len(const b200conv_t* h, int channel);    /* post-trim tap count            */
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 unsigned long long b200conv_launch_count(const b200conv_t* h);
+/* Tuning / A-B switches: "rt" (1 = real-time calls that stay inside the open block run as ONE cluster-kernel launch
+ * with zero-copy I/O, 0 = multi-kernel path), "fft512" (1 = register-resident FFT kernels for block size 512). */
+int    b200conv_set_option(b200conv_t* h, const char* name, int value);
 /* Device time (ms) spent in the dominant CMAC kernel / all kernels during the last
  * b200conv_process_device call, measured with CUDA events on the handle's stream
  * (enabled by b200conv_set_timing(h, 1); adds two event records per kernel). */

@@ -58,6 +58,7 @@ SYMBOLS = [
     ("b200conv_set_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("b200conv_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("b200conv_stream", C.c_void_p, [C.c_void_p]),
+    ("b200conv_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     ("b200conv_set_reduce", C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
     ("b200conv_prime", C.c_int, [C.c_void_p, _PP, C.c_size_t]),
     ("b200conv_process_xfade", C.c_int, [C.c_void_p, C.c_void_p, _PP, _PP, C.c_size_t, C.c_float, C.c_float]),

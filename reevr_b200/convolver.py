@@ -154,6 +154,10 @@ class Engine:
     def stream(self) -> int:
         return int(self._l.b200conv_stream(self._h) or 0)
 
+    def set_option(self, name: str, value: int):
+        """A/B switches of the engine: "rt" (one-launch real-time path), "fft512" (register-resident B = 512 FFTs)."""
+        self._check(self._l.b200conv_set_option(self._h, name.encode(), int(value)), "set_option")
+
     def set_timing(self, on: bool):
         self._l.b200conv_set_timing(self._h, int(on))
 

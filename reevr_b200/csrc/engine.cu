@@ -40,6 +40,7 @@
 #include "kernels.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_fft512.cuh"
+#include "kernels_rt.cuh"
 
 namespace {
 
@@ -75,8 +76,15 @@ struct Stage {
   cudaEvent_t ev_post[2] = {nullptr, nullptr};    // Y[b] no longer needed by reduce / inverse FFT
   float2* tw = nullptr;
   float2* tab512 = nullptr;   // B == 512: tables of the register-resident FFT kernels
-  float* inbuf = nullptr;
+  float* inbuf = nullptr;           // open block of this stage (+ the current call's samples on the batch path)
+  float* inbuf_alt = nullptr;       // stages >= 1: second buffer — a tail block enqueued on s_tail keeps reading the
+                                    // one it completed while the following calls already fill the other
   size_t in_stride = 0;
+  // tail blocks enqueued on the low-priority stream by the real-time path (stages >= 1)
+  cudaEvent_t ev_job[2] = {nullptr, nullptr};
+  long long job_out_start[2] = {0, 0};   // absolute sample position where the job's output is first needed
+  bool job_waited[2] = {true, true};
+  unsigned long long njobs = 0;
   float* fut = nullptr;
   size_t ring = 0;
 };
@@ -95,6 +103,11 @@ struct b200conv {
   size_t Lmax = 0;                // max samples per launch group
   long long abs_pos = 0;          // absolute stream position (samples since init/clear)
   cudaStream_t s_main = nullptr, s_post = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_tail = nullptr;     // lowest priority: tail-stage blocks of the real-time path (run_tail_block)
+  cudaStream_t s_launch = nullptr;   // stream the kernel launchers use: s_main, or s_tail while a tail block is enqueued
+  cudaEvent_t ev_rt = nullptr;       // real-time kernel of the current call done (s_main)
+  float* hpin_in_dev = nullptr;      // device-side addresses of the pinned staging buffers (zero-copy I/O)
+  float* hpin_out_dev = nullptr;
   cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{}, ev_din[2]{};
   cudaEvent_t ev_join = nullptr;
   float* din[2] = {nullptr, nullptr};
@@ -122,6 +135,9 @@ struct b200conv {
   // time-slice sharding: Y row 0 (the overlap state, spectrum of the last completed block) does not belong to
   // the block in front of the open one any more (the timeline was advanced by forward FFTs only)
   bool yprev_stale = false;
+  // tuning / A-B switches (b200conv_set_option; defaults from the environment)
+  bool opt_rt = std::getenv("B200CONV_NO_RT") == nullptr;
+  bool opt_fft512 = std::getenv("B200CONV_NO_FFT512") == nullptr;
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -188,8 +204,9 @@ int cuda_fail(b200conv* h, cudaError_t e, const char* what) {
 int fail(b200conv* h, int code, const std::string& msg) { h->err = msg; return code; }
 
 void free_stage(Stage& s) {
-  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y[0]); cudaFree(s.Y[1]); cudaFree(s.tw); cudaFree(s.tab512); cudaFree(s.inbuf); cudaFree(s.fut);
+  cudaFree(s.H); cudaFree(s.X); cudaFree(s.Y[0]); cudaFree(s.Y[1]); cudaFree(s.tw); cudaFree(s.tab512); cudaFree(s.inbuf); cudaFree(s.inbuf_alt); cudaFree(s.fut);
   for (int i = 0; i < 2; ++i) {
+    if (s.ev_job[i]) cudaEventDestroy(s.ev_job[i]);
     if (s.ev_sweep[i]) cudaEventDestroy(s.ev_sweep[i]);
     if (s.ev_post[i]) cudaEventDestroy(s.ev_post[i]);
   }
@@ -219,6 +236,7 @@ void free_all(b200conv* h) {
   if (h->hpin_in) cudaFreeHost(h->hpin_in);
   if (h->hpin_out) cudaFreeHost(h->hpin_out);
   h->hpin_in = h->hpin_out = nullptr; h->hpin_cap = 0;
+  h->hpin_in_dev = h->hpin_out_dev = nullptr;
   h->ir_len.assign(h->C, 0);
   h->abs_pos = 0;
   h->Lmax = 0;
@@ -228,7 +246,7 @@ void free_all(b200conv* h) {
 enum { kKindFft = 0, kKindCmac = 1, kKindIfft = 2 };
 
 int timing_begin(b200conv* h, int kind, cudaStream_t st = nullptr) {
-  if (!st) st = h->s_main;
+  if (!st) st = h->s_launch;
   if (!h->timing) return -1;
   if (h->ev_used == h->ev_pool.size()) {
     EventPair p;
@@ -241,7 +259,7 @@ int timing_begin(b200conv* h, int kind, cudaStream_t st = nullptr) {
   return id;
 }
 void timing_end(b200conv* h, int id, cudaStream_t st = nullptr) {
-  if (id >= 0) cudaEventRecord(h->ev_pool[id].b, st ? st : h->s_main);
+  if (id >= 0) cudaEventRecord(h->ev_pool[id].b, st ? st : h->s_launch);
 }
 void timing_collect(b200conv* h) {
   h->t_cmac = h->t_fft = h->t_ifft = 0;
@@ -321,9 +339,7 @@ constexpr int kF512MinTransforms = 32;
 constexpr size_t kF512Smem = (size_t)(pc::kF512_TabLen + 8 * pc::kF512_Xch) * sizeof(float2);
 
 bool use_fft512(const b200conv* h, int M, int nblocks, int C, const float2* tab) {
-  (void)h;
-  static const bool off = std::getenv("B200CONV_NO_FFT512") != nullptr;      // A/B switch for tuning runs
-  return !off && M == pc::kF512_M && tab != nullptr && (long long)nblocks * C >= kF512MinTransforms;
+  return h->opt_fft512 && M == pc::kF512_M && tab != nullptr && (long long)nblocks * C >= kF512MinTransforms;
 }
 
 int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
@@ -333,7 +349,7 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
     pc::emu_fwd_fft512(P.nblocks, C, P, P.tab512);
 #else
     const int gx = std::max(1, std::min((P.nblocks + 7) / 8, (4 * h->n_sm + C - 1) / C));
-    pc::k_fwd_fft512<<<dim3(gx, C, 1), dim3(32, 8, 1), kF512Smem, h->s_main>>>(P, P.tab512);
+    pc::k_fwd_fft512<<<dim3(gx, C, 1), dim3(32, 8, 1), kF512Smem, h->s_launch>>>(P, P.tab512);
 #endif
     timing_end(h, id);
     h->launches++;
@@ -346,7 +362,7 @@ int launch_fwd(b200conv* h, const pc::FwdParams& P, int C) {
   pc::emu_fwd_fft({(int)g.grid.x, (int)g.grid.y, 1}, {(int)g.block.x, (int)g.block.y, 1}, P);
 #else
   switch (pc::ilog2(P.M)) {
-#define PC_CASE(L) case L: launch_fwd_l<L>(P, g, h->s_main); break;
+#define PC_CASE(L) case L: launch_fwd_l<L>(P, g, h->s_launch); break;
     PC_FOR_EACH_LOG2(PC_CASE)
 #undef PC_CASE
     default: return fail(h, B200CONV_EINVAL, "unsupported transform size");
@@ -403,7 +419,7 @@ void launch_cmac_t(b200conv* h, pc::CmacParams P, int C) {
   (void)block;
   pc::emu_cmac_batch<TT, D, TW>({(int)grid.x, (int)grid.y, (int)grid.z}, P);
 #else
-  pc::k_cmac_batch<TT, D, TW, BS><<<grid, block, 0, h->s_main>>>(P);
+  pc::k_cmac_batch<TT, D, TW, BS><<<grid, block, 0, h->s_launch>>>(P);
 #endif
 }
 
@@ -416,7 +432,7 @@ void launch_cmac2_t(b200conv* h, pc::CmacParams P, int C) {
   (void)block;
   pc::emu_cmac_batch2<TT, D, TW>({(int)grid.x, (int)grid.y, (int)grid.z}, P);
 #else
-  pc::k_cmac_batch2<TT, D, TW, BS, MINB><<<grid, block, 0, h->s_main>>>(P);
+  pc::k_cmac_batch2<TT, D, TW, BS, MINB><<<grid, block, 0, h->s_launch>>>(P);
 #endif
 }
 
@@ -457,7 +473,7 @@ int launch_cmac_stream(b200conv* h, const pc::CmacParams& P, int C) {
   S.nsplit = nsplit;
   if (nsplit > 1) {
     // rows [yrow0, yrow0+nb) of every channel are contiguous (row pitch C*B)
-    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_launch));
   }
   dim3 grid(ktiles, nsplit, C), block(32, kStreamPW, 1);
   int id = timing_begin(h, kKindCmac);
@@ -465,7 +481,7 @@ int launch_cmac_stream(b200conv* h, const pc::CmacParams& P, int C) {
   (void)block;
   pc::emu_cmac_stream<kStreamNBS, kStreamPW>({(int)grid.x, (int)grid.y, (int)grid.z}, S);
 #else
-  pc::k_cmac_stream<kStreamNBS, kStreamPW><<<grid, block, 0, h->s_main>>>(S);
+  pc::k_cmac_stream<kStreamNBS, kStreamPW><<<grid, block, 0, h->s_launch>>>(S);
 #endif
   timing_end(h, id);
   h->launches++;
@@ -478,7 +494,7 @@ void launch_stream_rows_t(b200conv* h, const pc::StreamParams& S, dim3 grid, int
 #if defined(PC_EMULATE)
   pc::emu_cmac_stream_rows<NB, U>({(int)grid.x, (int)grid.y, (int)grid.z}, threads, S);
 #else
-  pc::k_cmac_stream_rows<NB, U><<<grid, dim3(threads, 1, 1), 0, h->s_main>>>(S);
+  pc::k_cmac_stream_rows<NB, U><<<grid, dim3(threads, 1, 1), 0, h->s_launch>>>(S);
 #endif
 }
 
@@ -496,7 +512,7 @@ int launch_cmac_stream_rows(b200conv* h, const pc::CmacParams& P, int C) {
   nsplit = std::max(1, std::min(nsplit, std::max(1, P.Ppad / 8)));
   S.nsplit = nsplit;
   if (nsplit > 1)
-    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)P.nblocks * S.y_rstride * sizeof(float2), h->s_launch));
   dim3 grid(xt, nsplit, C);
   int id = timing_begin(h, kKindCmac);
   if (P.nblocks <= 1) launch_stream_rows_t<1, 8>(h, S, grid, threads);
@@ -516,7 +532,7 @@ int launch_stream_tma_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
   pc::emu_cmac_stream_tma({(int)grid.x, (int)grid.y, (int)grid.z}, S_);
 #else
   const size_t smem = (size_t)S * pc::kStreamStageBytes + 16 * S;
-  pc::k_cmac_stream_tma<S><<<grid, dim3(288, 1, 1), smem, h->s_main>>>(S_);
+  pc::k_cmac_stream_tma<S><<<grid, dim3(288, 1, 1), smem, h->s_launch>>>(S_);
 #endif
   return 0;
 }
@@ -534,7 +550,7 @@ int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stag
   nsplit = std::max(1, std::min(nsplit, std::max(1, P.Ppad / (2 * PP))));
   S.nsplit = nsplit;
   if (nsplit > 1 || RG > 1)
-    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_launch));
   dim3 grid(xt, nsplit, C);
   int id = timing_begin(h, kKindCmac);
   switch (stages) {
@@ -725,11 +741,14 @@ int alloc_stage_state(b200conv* h, Stage& s) {
   if (s.q > 0) {
     s.ring = next_pow2((size_t)(s.q + 2) * B + h->Lmax + B);
     CU_CHECK(h, cudaMalloc(&s.fut, (size_t)C * s.ring * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&s.inbuf_alt, (size_t)C * s.in_stride * sizeof(float)));
+    for (int i = 0; i < 2; ++i) CU_CHECK(h, cudaEventCreateWithFlags(&s.ev_job[i], cudaEventDisableTiming));
   }
   return 0;
 }
 
 int clear_state(b200conv* h) {
+  if (h->s_tail) CU_CHECK(h, cudaStreamSynchronize(h->s_tail));
   CU_CHECK(h, cudaStreamSynchronize(h->s_post));
   for (auto& s : h->stages) {
     const int C = h->C, B = s.B;
@@ -738,7 +757,10 @@ int clear_state(b200conv* h) {
       CU_CHECK(h, cudaMemsetAsync(s.Y[i], 0, (size_t)(1 + s.Tcap) * C * B * sizeof(float2), h->s_main));
     s.ybuf = 0;
     CU_CHECK(h, cudaMemsetAsync(s.inbuf, 0, (size_t)C * s.in_stride * sizeof(float), h->s_main));
+    if (s.inbuf_alt) CU_CHECK(h, cudaMemsetAsync(s.inbuf_alt, 0, (size_t)C * s.in_stride * sizeof(float), h->s_main));
     if (s.fut) CU_CHECK(h, cudaMemsetAsync(s.fut, 0, (size_t)C * s.ring * sizeof(float), h->s_main));
+    s.job_waited[0] = s.job_waited[1] = true;
+    s.njobs = 0;
     s.head = s.hist;
     s.blocks_done = 0;
     s.fill = 0;
@@ -760,6 +782,7 @@ int init_impl(b200conv* h, int n_stages, const size_t* blocks, const size_t* off
   if (int rc = set_device(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   CU_CHECK(h, cudaStreamSynchronize(h->s_post));
+  if (h->s_tail) CU_CHECK(h, cudaStreamSynchronize(h->s_tail));
   free_all(h);
   const int C = h->C;
   for (int s = 0; s < n_stages; ++s)
@@ -810,6 +833,15 @@ int init_impl(b200conv* h, int n_stages, const size_t* blocks, const size_t* off
   h->hpin_cap = std::min(h->Lmax, std::max((size_t)64 * B0, (size_t)16384));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_in, (size_t)C * h->hpin_cap * sizeof(float)));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_out, (size_t)C * h->hpin_cap * sizeof(float)));
+#if defined(PC_EMULATE)
+  h->hpin_in_dev = h->hpin_in; h->hpin_out_dev = h->hpin_out;
+#else
+  if (cudaHostGetDevicePointer((void**)&h->hpin_in_dev, h->hpin_in, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&h->hpin_out_dev, h->hpin_out, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->hpin_in_dev = h->hpin_out_dev = nullptr;       // no zero-copy I/O: the real-time path stays on the copy path
+  }
+#endif
   if (int rc = clear_state(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return B200CONV_OK;
@@ -884,7 +916,7 @@ int compact_timeline(b200conv* h, Stage& s) {
   const size_t bytes = (size_t)s.hist * B * sizeof(float2);
   for (int c = 0; c < C; ++c) {
     float2* base = s.X + (size_t)c * s.R * B;
-    CU_CHECK(h, cudaMemcpyAsync(base, base + (size_t)(s.head - s.hist) * B, bytes, cudaMemcpyDeviceToDevice, h->s_main));
+    CU_CHECK(h, cudaMemcpyAsync(base, base + (size_t)(s.head - s.hist) * B, bytes, cudaMemcpyDeviceToDevice, h->s_launch));
   }
   s.head = s.hist;
   return 0;
@@ -1096,6 +1128,8 @@ int run_group_p2p(b200conv* h, const float* in_dev, size_t in_stride, float* out
   return 0;
 }
 
+int drain_tail(b200conv* h);
+
 // `overlap`: reduce + inverse FFT go to s_post so that they overlap the next group's forward
 // FFT + sweep on s_main (double-buffered Y); otherwise everything is issued on s_main.
 int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev, size_t out_stride, size_t n,
@@ -1109,6 +1143,7 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
   cudaStream_t ps = overlap ? h->s_post : h->s_main;
   if (n == 0) return 0;
   if (n + h->stages[0].B > h->Lmax) return fail(h, B200CONV_ESTATE, "launch group larger than the staging buffers");
+  if (int rc = drain_tail(h)) return rc;
   // stages >= 1 first (their look-ahead output may be consumed by the head within this group)
   for (int si = (int)h->stages.size() - 1; si >= 0; --si) {
     Stage& s = h->stages[si];
@@ -1272,6 +1307,178 @@ int plan_slice(b200conv* h, size_t len, int rank, int count, SlicePlan* sp) {
   return 0;
 }
 
+// ---- real-time path: one cluster kernel per call (kernels_rt.cuh) + tail blocks on the low-priority stream -----
+// every batch-path entry point first orders s_main (and s_post) behind all tail blocks still in flight on s_tail
+int drain_tail(b200conv* h) {
+  for (auto& s : h->stages)
+    for (int j = 0; j < 2; ++j)
+      if (!s.job_waited[j]) {
+        CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_job[j], 0));
+        CU_CHECK(h, cudaStreamWaitEvent(h->s_post, s.ev_job[j], 0));
+        s.job_waited[j] = true;
+      }
+  return 0;
+}
+
+// ONE completed block of a stage >= 1 (its samples are in s.inbuf), everything on h->s_launch: forward FFT into the
+// timeline, streaming sweep, inverse FFT into the stage's look-ahead ring (TwoStageFFTConvolver.cpp:201-222)
+int run_tail_block(b200conv* h, Stage& s) {
+  const int C = h->C, B = s.B;
+  const size_t row = (size_t)C * B;
+  cudaStream_t st = h->s_launch;
+  if (s.head + 1 + kMaxTT > s.R) { if (int rc = compact_timeline(h, s)) return rc; }
+  pc::FwdParams fp{};
+  fp.src = s.inbuf; fp.src_cstride = (long long)s.in_stride;
+  fp.nvalid_c = nullptr; fp.nvalid = (long long)B;
+  fp.dst = s.X; fp.dst_cstride = (long long)s.R * B; fp.dst_row0 = s.head;
+  fp.tw = s.tw; fp.tab512 = s.tab512; fp.M = B; fp.nblocks = 1;
+  if (int rc = launch_fwd(h, fp, C)) return rc;
+  float2* Yb = s.Y[s.ybuf];
+  pc::CmacParams cp{};
+  cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
+  cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
+  cp.Y = Yb; cp.y_cstride = B; cp.y_rstride = (long long)row; cp.yrow0 = 1;
+  cp.B = B; cp.Ppad = s.P; cp.nblocks = 1;
+  if (int rc = launch_cmac(h, cp, C)) return rc;
+  pc::InvParams ip{};
+  ip.Y = Yb; ip.y_cstride = B; ip.y_rstride = (long long)row; ip.yrow0 = 1;
+  ip.tw = s.tw; ip.tab512 = s.tab512; ip.M = B; ip.nblocks = 1; ip.scale = 1.0f / (float)B;
+  ip.dst = s.fut; ip.dst_cstride = (long long)s.ring;
+  ip.index0 = (s.blocks_done + s.q) * (long long)B;
+  ip.lo = 0; ip.hi = (long long)1 << 62; ip.mask = (long long)s.ring - 1;
+  ip.n_add = 0; ip.abs0 = 0;
+  if (int rc = launch_inv(h, ip, C, st)) return rc;
+  CU_CHECK(h, cudaMemcpyAsync(Yb, Yb + row, row * sizeof(float2), cudaMemcpyDeviceToDevice, st));   // overlap state
+  s.head += 1;
+  s.blocks_done += 1;
+  s.fill = 0;
+  return 0;
+}
+
+constexpr size_t kRtMaxBytesPerCta = 1280 * 1024;     // H + FDL bytes one CTA of the cluster may have to stream
+
+// CTAs per convolver for the cluster kernel, 0 = the call does not qualify
+int rt_cluster_ctas(const b200conv* h, size_t len) {
+  if (!h->opt_rt || h->stages.empty() || h->stages.size() > 4) return 0;
+  if (h->cfg.shard_count != 1 || h->p2p_on || h->timing || h->yprev_stale) return 0;
+  const Stage& s0 = h->stages[0];
+  const int M = s0.B, C = h->C;
+  if (M < 16 || M > 1024 || C > 16 || len == 0 || (size_t)s0.fill + len > (size_t)M) return 0;
+  if (h->route_on && (h->n_out * (int)len > 8 * 1024)) return 0;
+  int max_nc = 1;
+  while (max_nc * 2 * C <= 16 && max_nc * 2 <= M / 32) max_nc *= 2;     // cluster <= 16 CTAs, tile >= 16 bin pairs
+  int nc = 1;
+  while (M / nc / 2 > 256) nc *= 2;                                      // at most 256 bin pairs per CTA
+  const size_t bytes = (size_t)s0.P * M * 16;                            // H + FDL rows of one convolver
+  while (nc < max_nc && bytes / nc > 320 * 1024) nc *= 2;
+  if (nc > max_nc || bytes / nc > kRtMaxBytesPerCta) return 0;
+  return nc;
+}
+
+#if !defined(PC_EMULATE)
+template <int M>
+cudaError_t rt_launch_m(const pc::RtParams& P, int nctas, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nctas, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = nctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, pc::k_rt_block<M>, P);
+}
+template <int M>
+bool rt_set_attr() {
+  const int smem = pc::rt_smem_layout(M, 16).bytes;
+  return cudaFuncSetAttribute(pc::k_rt_block<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+         cudaFuncSetAttribute(pc::k_rt_block<M>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+}
+#endif
+
+// One real-time call (rt_cluster_ctas() > 0): `in` / `out` are device-accessible (pinned host or device memory).
+int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, size_t out_stride, size_t len) {
+  const int C = h->C;
+  Stage& s0 = h->stages[0];
+  const int M = s0.B;
+  // tail blocks whose output this call needs must have landed in their look-ahead rings
+  for (size_t si = 1; si < h->stages.size(); ++si) {
+    Stage& s = h->stages[si];
+    for (int j = 0; j < 2; ++j)
+      if (!s.job_waited[j] && h->abs_pos + (long long)len > s.job_out_start[j]) {
+        CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_job[j], 0));
+        s.job_waited[j] = true;
+      }
+  }
+  if (s0.head + 1 + kMaxTT > s0.R) { if (int rc = compact_timeline(h, s0)) return rc; }
+  pc::RtParams P{};
+  P.M = M; P.C = C; P.NC = nc; P.P = s0.P;
+  P.fill = s0.fill; P.len = (int)len; P.complete = (s0.fill + (int)len == M) ? 1 : 0;
+  P.in = in; P.in_stride = (long long)in_stride;
+  for (int c = 0; c < 8; ++c) P.in_map[c] = h->route_on ? h->in_map[c] : c;
+  if (C > 8) return fail(h, B200CONV_ESTATE, "real-time kernel supports up to 8 convolvers per handle");
+  P.inbuf0 = s0.inbuf; P.inbuf0_stride = (long long)s0.in_stride;
+  P.H = s0.H; P.h_cstride = (long long)s0.Prows * M;
+  P.X = s0.X; P.x_cstride = (long long)s0.R * M; P.head = s0.head;
+  P.Yprev = s0.Y[s0.ybuf]; P.Ynext = s0.Y[s0.ybuf ^ 1]; P.y_cstride = M;
+  P.tw = s0.tw;
+  int na = 0;
+  for (size_t si = 1; si < h->stages.size(); ++si) {
+    Stage& s = h->stages[si];
+    P.later_inbuf[na] = s.inbuf; P.later_stride[na] = (long long)s.in_stride; P.later_fill[na] = s.fill;
+    P.add[na] = s.fut; P.add_cstride[na] = (long long)s.ring; P.add_mask[na] = (long long)s.ring - 1;
+    ++na;
+  }
+  P.n_later = na; P.n_add = na;
+  P.abs0 = h->abs_pos - s0.fill;
+  P.out = out; P.out_stride = (long long)out_stride;
+  P.mix_on = h->route_on ? 1 : 0; P.n_out = h->route_on ? h->n_out : C;
+  std::memcpy(P.mix, h->mix, sizeof(P.mix));
+#if defined(PC_EMULATE)
+  pc::emu_rt_block(P);
+#else
+  const size_t smem = (size_t)pc::rt_smem_layout(M, C).bytes;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (M) {
+    case 16: e = rt_launch_m<16>(P, C * nc, smem, h->s_main); break;
+    case 32: e = rt_launch_m<32>(P, C * nc, smem, h->s_main); break;
+    case 64: e = rt_launch_m<64>(P, C * nc, smem, h->s_main); break;
+    case 128: e = rt_launch_m<128>(P, C * nc, smem, h->s_main); break;
+    case 256: e = rt_launch_m<256>(P, C * nc, smem, h->s_main); break;
+    case 512: e = rt_launch_m<512>(P, C * nc, smem, h->s_main); break;
+    case 1024: e = rt_launch_m<1024>(P, C * nc, smem, h->s_main); break;
+    default: break;
+  }
+  CU_CHECK(h, e);
+#endif
+  h->launches++;
+  // bookkeeping of the head stage
+  if (P.complete) { s0.head += 1; s0.blocks_done += 1; s0.fill = 0; s0.ybuf ^= 1; }
+  else s0.fill += (int)len;
+  h->abs_pos += (long long)len;
+  // later stages: the kernel appended the samples; a completed block goes to the low-priority stream
+  bool recorded = false;
+  for (size_t si = 1; si < h->stages.size(); ++si) {
+    Stage& s = h->stages[si];
+    s.fill += (int)len;
+    if (s.fill < s.B) continue;
+    if (!recorded) { CU_CHECK(h, cudaEventRecord(h->ev_rt, h->s_main)); recorded = true; }
+    CU_CHECK(h, cudaStreamWaitEvent(h->s_tail, h->ev_rt, 0));
+    const int j = (int)(s.njobs & 1);
+    s.job_out_start[j] = (s.blocks_done + s.q) * (long long)s.B;
+    h->s_launch = h->s_tail;
+    const int rc = run_tail_block(h, s);
+    h->s_launch = h->s_main;
+    if (rc) return rc;
+    CU_CHECK(h, cudaEventRecord(s.ev_job[j], h->s_tail));
+    s.job_waited[j] = false;
+    s.njobs++;
+    std::swap(s.inbuf, s.inbuf_alt);              // the following calls fill the other buffer
+  }
+  return 0;
+}
+
 // make s_main wait for everything queued on s_post (end of an overlapped call)
 int join_post(b200conv* h) {
   CU_CHECK(h, cudaEventRecord(h->ev_join, h->s_post));
@@ -1320,6 +1527,11 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
 #endif
   bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, hi) == cudaSuccess;
   ok = ok && cudaStreamCreateWithPriority(&h->s_post, cudaStreamNonBlocking, hi) == cudaSuccess;
+  // tail blocks have a whole tail period (8192 samples = 171 ms at 48 kHz) to finish: lowest priority, so that they
+  // never delay the head-stage kernels of this or any other handle (TwoStageFFTConvolver.cpp:213-222, Convolver.cpp:84-95)
+  ok = ok && cudaStreamCreateWithPriority(&h->s_tail, cudaStreamNonBlocking, lo) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_rt, cudaEventDisableTiming) == cudaSuccess;
+  h->s_launch = h->s_main;
   ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -1339,6 +1551,8 @@ b200conv_t* b200conv_create(const b200conv_config* cfg) {
       PC_FOR_EACH_LOG2(PC_CASE)
 #undef PC_CASE
       attr_ok = attr_ok && stream_set_smem_attr();
+      attr_ok = attr_ok && rt_set_attr<16>() && rt_set_attr<32>() && rt_set_attr<64>() && rt_set_attr<128>() &&
+                rt_set_attr<256>() && rt_set_attr<512>() && rt_set_attr<1024>();
       attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_fwd_fft512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
       attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_inv_fft512<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
       attr_ok = attr_ok && cudaFuncSetAttribute(pc::k_inv_fft512<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF512Smem) == cudaSuccess;
@@ -1359,7 +1573,10 @@ void b200conv_destroy(b200conv_t* h) {
     cudaSetDevice(h->cfg.device);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_post) cudaStreamSynchronize(h->s_post);
+    if (h->s_tail) cudaStreamSynchronize(h->s_tail);
     free_all(h);
+    if (h->ev_rt) cudaEventDestroy(h->ev_rt);
+    if (h->s_tail) cudaStreamDestroy(h->s_tail);
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {
       if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -1429,6 +1646,10 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
     const size_t chunk = h->Lmax - B0;     // keeps fill + n <= Lmax for every stage (inbuf holds B + Lmax samples)
     const bool overlap = len > chunk || h->cfg.shard_count > 1;    // (slot-exchange groups always use s_post)
     size_t done = 0;
+    if (const int nc = rt_cluster_ctas(h, len)) {       // a call inside the open block: one cluster kernel
+      if (int rc = rt_call(h, nc, in_dev, in_stride, out_dev, out_stride, len)) return rc;
+      done = len;
+    }
     while (done < len) {
       size_t n = std::min(len - done, chunk);
       if (int rc = run_group(h, in_dev + done, in_stride, out_dev + done, out_stride, n, overlap)) return rc;
@@ -1488,6 +1709,16 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
   const size_t B0 = h->stages[0].B;
   const size_t chunk = h->Lmax - B0;
   if (len <= chunk && len <= std::max((size_t)64 * B0, (size_t)16384)) {
+    if (const int nc = (len <= h->hpin_cap && h->hpin_in_dev && h->hpin_out_dev) ? rt_cluster_ctas(h, len) : 0) {
+      // real-time path: the cluster kernel reads the samples straight from the pinned staging buffer and writes the
+      // result into it (zero-copy over PCIe): one launch + one synchronise per call
+      for (int c = 0; c < Cin; ++c) std::memcpy(h->hpin_in + (size_t)c * len, in[c], len * sizeof(float));
+      if (int rc = rt_call(h, nc, h->hpin_in_dev, len, h->hpin_out_dev, len, len)) return rc;
+      CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+      if (out)
+        for (int c = 0; c < Cout; ++c) std::memcpy(out[c], h->hpin_out + (size_t)c * len, len * sizeof(float));
+      return B200CONV_OK;
+    }
     // latency path: one stream, one group; all channels travel in ONE pinned H2D and ONE D2H copy
     // (channel pitch = len), which matters for the 2-4 channel handles of a StereoConvolver
     const bool packed = len <= h->hpin_cap;
@@ -1753,6 +1984,7 @@ int b200conv_reset(b200conv_t* h) {
   if (int rc = set_device(h)) return rc;
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   CU_CHECK(h, cudaStreamSynchronize(h->s_post));
+  if (h->s_tail) CU_CHECK(h, cudaStreamSynchronize(h->s_tail));
   free_all(h);
   return B200CONV_OK;
 }
@@ -1773,6 +2005,15 @@ size_t b200conv_ir_len(const b200conv_t* h, int channel) {
 }
 
 unsigned long long b200conv_launch_count(const b200conv_t* h) { return h ? h->launches : 0; }
+
+int b200conv_set_option(b200conv_t* h, const char* name, int value) {
+  if (!h || !name) return B200CONV_EINVAL;
+  const std::string n(name);
+  if (n == "rt") h->opt_rt = value != 0;
+  else if (n == "fft512") h->opt_fft512 = value != 0;
+  else return fail(h, B200CONV_EINVAL, "unknown option");
+  return B200CONV_OK;
+}
 
 int b200conv_set_timing(b200conv_t* h, int enable) {
   if (!h) return B200CONV_EINVAL;

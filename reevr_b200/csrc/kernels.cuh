@@ -36,6 +36,8 @@
 #define PC_HD inline
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 #endif
 
 namespace pc {

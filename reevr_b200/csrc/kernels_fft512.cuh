@@ -15,8 +15,9 @@
 //   step 2  DFT8 over n1 for the two pairs (k2, n0) = (pid / 8, pid % 8), pid in {lane, lane + 32} -> twiddle W64^{n0 q0}
 //   step 3  DFT8 over n0 for the two residues l = k2 + 8 q0 in {lane, 64 - lane}  (lane 0: {0, 32})
 //
-// with two exchanges through ONE 4.5 KB shared buffer per warp (row pitches 72 / 66 float2: conflict-free for the
-// access patterns below) and __syncwarp() only.  Everything that touches global memory is coalesced: for a fixed
+// with two exchanges through ONE 4 KB shared buffer per warp (XOR-swizzled so that both the writing and the reading
+// side of each exchange are bank-conflict free: every half-warp of a 64-bit access touches 16 distinct bank pairs)
+// and __syncwarp() only.  Everything that touches global memory is coalesced: for a fixed
 // register index consecutive lanes hold consecutive points (first step: consecutive columns; last step: consecutive /
 // mirrored residues).  The lane that owns residue l also owns 64 - l, i.e. bins k and M - k of every mirror pair, so
 // the even/odd split of the real transform (and its inverse, merged with the frequency-domain overlap-add) needs no
@@ -36,7 +37,7 @@ namespace pc {
 
 constexpr int kF512_M = 512;
 constexpr int kF512_T1 = 0, kF512_T2 = 512, kF512_TS = 576, kF512_TabLen = 1088;
-constexpr int kF512_Xch = 8 * 72;       // float2 per warp exchange buffer
+constexpr int kF512_Xch = 512;          // float2 per warp exchange buffer
 
 // complex add / sub / scale on float2: on the device these are single packed-FP32 instructions (FADD2 / FFMA2)
 PC_HD float2 f2_add(float2 a, float2 b) {
@@ -104,9 +105,13 @@ PC_HD void f512_dft8(float2* a) {
 // residues owned by a lane in step 3 (and, mirrored, in the first inverse step)
 PC_HD int f512_la(int lane) { return lane; }
 PC_HD int f512_lb(int lane) { return lane == 0 ? 32 : 64 - lane; }
-// exchange-buffer layouts
-PC_HD int f512_s1(int k2, int m) { return k2 * 72 + m; }                       // [k2][m = 8 n1 + n0]
-PC_HD int f512_s2(int k2, int q0, int n0) { return k2 * 66 + 8 * q0 + n0; }    // [k2][q0][n0]
+// exchange-buffer layouts (float2 index; 16 consecutive float2 = the 32 banks).
+// s1 [k2][m = 8 n1 + n0]: written with consecutive m per k2, read with (k2, k2 + 1) x n0 = 0..7 per half-warp at a
+//    fixed n1 -> bit 3 of m is flipped for odd k2 so that the two k2 land in different halves of the bank set.
+// s2 [k2][q0][n0]: written with (k2, k2 + 1) x n0 = 0..7 at a fixed q0, read with k2 = 0..7 x (q0, q0 + 1) at a fixed
+//    n0 -> n0 ^ k2 spreads the eight k2 over eight bank pairs, bit 0 of q0 ^ k2 picks the half.
+PC_HD int f512_s1(int k2, int m) { return k2 * 64 + (m ^ ((k2 & 1) << 3)); }
+PC_HD int f512_s2(int k2, int q0, int n0) { return k2 * 64 + ((q0 ^ (k2 & 1)) << 3) + (n0 ^ k2); }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward: z[n] = (x[2n], x[2n+1]), n < 256 valid (the upper half of [x ; 0] is zero)
@@ -148,7 +153,10 @@ PC_HD void f512_mid_load(int lane, const float2* S, const float2* tab, float2* A
     f512_dft8<INV>(a);
     // forward: C[q0] *= W64^{n0 q0} ; inverse: E[n1] *= conj(W64^{n1 k2})
 #pragma unroll
-    for (int j = 1; j < 8; ++j) a[j] = f2_cmul<INV>(a[j], tab[kF512_T2 + (INV ? j * 8 + k2 : n0 * 8 + j)]);
+    // (T2 is symmetric, W64^{ab} = W64^{ba}: index it row-major in the loop variable so that the 8 distinct
+    //  addresses of an instruction are consecutive words)
+#pragma unroll
+    for (int j = 1; j < 8; ++j) a[j] = f2_cmul<INV>(a[j], tab[kF512_T2 + j * 8 + (INV ? k2 : n0)]);
   }
 }
 template <bool INV>
@@ -290,7 +298,7 @@ PC_HD void f512_inv_p3(int lane, const float2* S, float scale, const OutSpec& o)
 
 #if defined(__CUDACC__)
 // grid (ceil(nblocks / 8) capped, C), block (32, 8): warp = one transform, looping over blocks with stride 8 * gridDim.x
-// dynamic smem = (1088 + 8 * 576) float2 = 45568 bytes
+// dynamic smem = (1088 + 8 * 512) float2 = 41472 bytes
 __global__ void __launch_bounds__(256, 4) k_fwd_fft512(FwdParams P, const float2* __restrict__ tab512) {
   extern __shared__ float2 pc_smem512[];
   float2* tab = pc_smem512;

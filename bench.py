@@ -420,6 +420,7 @@ def main():
     # ---- host buffers: ONE page-locked region all ranks see (memfd + cudaHostRegister) so that every GPU can
     #      read its input slice from, and write its output slice into, the caller's buffers directly
     keep_alive = []
+    registered = []          # (address, mmap, fd) of the shared page-locked regions: unregistered before exit
 
     def host_buffers(shape, tag):
         """returns (np array, shared?) — all ranks agree on `shared`"""
@@ -439,8 +440,12 @@ def main():
                 arr = np.frombuffer(mm, dtype=np.float32).reshape(shape)
                 if rank == 0:
                     arr[...] = 0                 # first touch on rank 0's node
-                if lib.b200conv_register_host(arr.ctypes.data, nbytes) != 0:
+                if os.environ.get("B200CONV_BENCH_NO_SHARED"):
                     ok = 0
+                elif lib.b200conv_register_host(arr.ctypes.data, nbytes) != 0:
+                    ok = 0
+                else:
+                    registered.append(arr.ctypes.data)
                 keep_alive.append((mm, fd))
             except Exception as ex:
                 print(f"[bench] rank {rank}: shared host buffer failed ({type(ex).__name__}: {ex})", file=sys.stderr)
@@ -895,6 +900,15 @@ def main():
             if p and not p.get("ok", True):
                 print(f"[bench] PARITY FAILURE ({name}): {p}", file=sys.stderr)
                 rc_exit = 3
+    # orderly teardown: nothing in flight, page-locked shared regions unregistered while the context is still alive
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for addr in registered:
+        lib.b200conv_unregister_host(addr)
+    del flush
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

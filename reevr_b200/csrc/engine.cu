@@ -28,6 +28,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -108,6 +109,9 @@ struct b200conv {
   cudaEvent_t ev_rt = nullptr;       // real-time kernel of the current call done (s_main)
   float* hpin_in_dev = nullptr;      // device-side addresses of the pinned staging buffers (zero-copy I/O)
   float* hpin_out_dev = nullptr;
+  unsigned int* hflag = nullptr;     // pinned completion word of the real-time kernel (+ its device-side address)
+  unsigned int* hflag_dev = nullptr;
+  unsigned int flag_epoch = 0;
   cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{}, ev_din[2]{};
   cudaEvent_t ev_join = nullptr;
   float* din[2] = {nullptr, nullptr};
@@ -235,6 +239,8 @@ void free_all(b200conv* h) {
   cudaFree(h->dch[0]); h->dch[0] = nullptr;
   if (h->hpin_in) cudaFreeHost(h->hpin_in);
   if (h->hpin_out) cudaFreeHost(h->hpin_out);
+  if (h->hflag) cudaFreeHost(h->hflag);
+  h->hflag = h->hflag_dev = nullptr;
   h->hpin_in = h->hpin_out = nullptr; h->hpin_cap = 0;
   h->hpin_in_dev = h->hpin_out_dev = nullptr;
   h->ir_len.assign(h->C, 0);
@@ -833,9 +839,12 @@ int init_impl(b200conv* h, int n_stages, const size_t* blocks, const size_t* off
   h->hpin_cap = std::min(h->Lmax, std::max((size_t)64 * B0, (size_t)16384));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_in, (size_t)C * h->hpin_cap * sizeof(float)));
   CU_CHECK(h, cudaMallocHost((void**)&h->hpin_out, (size_t)C * h->hpin_cap * sizeof(float)));
+  CU_CHECK(h, cudaMallocHost((void**)&h->hflag, 64));
+  *h->hflag = 0; h->flag_epoch = 0;
 #if defined(PC_EMULATE)
-  h->hpin_in_dev = h->hpin_in; h->hpin_out_dev = h->hpin_out;
+  h->hpin_in_dev = h->hpin_in; h->hpin_out_dev = h->hpin_out; h->hflag_dev = h->hflag;
 #else
+  if (cudaHostGetDevicePointer((void**)&h->hflag_dev, h->hflag, 0) != cudaSuccess) { cudaGetLastError(); h->hflag_dev = nullptr; }
   if (cudaHostGetDevicePointer((void**)&h->hpin_in_dev, h->hpin_in, 0) != cudaSuccess ||
       cudaHostGetDevicePointer((void**)&h->hpin_out_dev, h->hpin_out, 0) != cudaSuccess) {
     cudaGetLastError();
@@ -1014,7 +1023,7 @@ int p2p_barrier(b200conv* h, cudaStream_t st, int bank = 0) {
     static const unsigned long long timeout_ms = [] {
       const char* e = std::getenv("B200CONV_P2P_TIMEOUT_MS");
       const long long v = e ? std::atoll(e) : 0;
-      return (unsigned long long)(v > 0 ? v : 20000);      // default 20 s: a peer may be loading modules / paging in
+      return (unsigned long long)(v > 0 ? v : 4000);       // default 4 s (every kernel of the exchange is pre-loaded at attach)
     }();
     bp.timeout_ns = timeout_ms * 1000000ull;
   }
@@ -1355,7 +1364,7 @@ int run_tail_block(b200conv* h, Stage& s) {
   return 0;
 }
 
-constexpr size_t kRtMaxBytesPerCta = 1280 * 1024;     // H + FDL bytes one CTA of the cluster may have to stream
+constexpr size_t kRtMaxBytesPerCta = 384 * 1024;      // H + FDL bytes one CTA of the cluster may have to stream
 
 // CTAs per convolver for the cluster kernel, 0 = the call does not qualify
 int rt_cluster_ctas(const b200conv* h, size_t len) {
@@ -1370,7 +1379,9 @@ int rt_cluster_ctas(const b200conv* h, size_t len) {
   int nc = 1;
   while (M / nc / 2 > 256) nc *= 2;                                      // at most 256 bin pairs per CTA
   const size_t bytes = (size_t)s0.P * M * 16;                            // H + FDL rows of one convolver
-  while (nc < max_nc && bytes / nc > 320 * 1024) nc *= 2;
+  // one SM pulls ~20-50 GB/s out of L2 with this access pattern: spread a convolver over as many CTAs as the
+  // cluster allows until a CTA streams <= 64 KB; beyond kRtMaxBytesPerCta the all-SM streaming sweep wins
+  while (nc < max_nc && bytes / nc > 64 * 1024) nc *= 2;
   if (nc > max_nc || bytes / nc > kRtMaxBytesPerCta) return 0;
   return nc;
 }
@@ -1398,7 +1409,7 @@ bool rt_set_attr() {
 #endif
 
 // One real-time call (rt_cluster_ctas() > 0): `in` / `out` are device-accessible (pinned host or device memory).
-int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, size_t out_stride, size_t len) {
+int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, size_t out_stride, size_t len, bool use_flag) {
   const int C = h->C;
   Stage& s0 = h->stages[0];
   const int M = s0.B;
@@ -1435,6 +1446,7 @@ int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, 
   P.out = out; P.out_stride = (long long)out_stride;
   P.mix_on = h->route_on ? 1 : 0; P.n_out = h->route_on ? h->n_out : C;
   std::memcpy(P.mix, h->mix, sizeof(P.mix));
+  if (use_flag && h->hflag_dev) { P.done_flag = h->hflag_dev; P.done_val = ++h->flag_epoch; }
 #if defined(PC_EMULATE)
   pc::emu_rt_block(P);
 #else
@@ -1647,7 +1659,7 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
     const bool overlap = len > chunk || h->cfg.shard_count > 1;    // (slot-exchange groups always use s_post)
     size_t done = 0;
     if (const int nc = rt_cluster_ctas(h, len)) {       // a call inside the open block: one cluster kernel
-      if (int rc = rt_call(h, nc, in_dev, in_stride, out_dev, out_stride, len)) return rc;
+      if (int rc = rt_call(h, nc, in_dev, in_stride, out_dev, out_stride, len, false)) return rc;
       done = len;
     }
     while (done < len) {
@@ -1713,8 +1725,19 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
       // real-time path: the cluster kernel reads the samples straight from the pinned staging buffer and writes the
       // result into it (zero-copy over PCIe): one launch + one synchronise per call
       for (int c = 0; c < Cin; ++c) std::memcpy(h->hpin_in + (size_t)c * len, in[c], len * sizeof(float));
-      if (int rc = rt_call(h, nc, h->hpin_in_dev, len, h->hpin_out_dev, len, len)) return rc;
-      CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+      if (int rc = rt_call(h, nc, h->hpin_in_dev, len, h->hpin_out_dev, len, len, true)) return rc;
+      // wait for the kernel's completion word (set after all output stores) instead of the driver's stream
+      // synchronise; if it does not show up within 20 ms, fall back to the synchronise (and its error report)
+      bool done = false;
+      if (h->hflag_dev) {
+        volatile unsigned int* f = h->hflag;
+        const unsigned int want = h->flag_epoch;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spins = 0; !(done = (*f == want)); ++spins)
+          if ((spins & 0x3ff) == 0x3ff &&
+              std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+      }
+      if (!done) CU_CHECK(h, cudaStreamSynchronize(h->s_main));
       if (out)
         for (int c = 0; c < Cout; ++c) std::memcpy(out[c], h->hpin_out + (size_t)c * len, len * sizeof(float));
       return B200CONV_OK;

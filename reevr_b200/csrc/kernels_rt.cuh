@@ -46,6 +46,9 @@ struct RtParams {
   // output: n_out mixed channels (mix_on) or C channels at out + o * out_stride
   float* out; long long out_stride;
   int mix_on, n_out; float mix[64];
+  // completion word in pinned host memory (nullptr: none): set to done_val once every output sample is written, so
+  // that the caller can spin on it instead of paying the driver's stream-synchronise latency
+  unsigned int* done_flag; unsigned int done_val;
 };
 
 // shared-memory layout of one CTA (float2 units unless noted)
@@ -120,25 +123,24 @@ PC_HD float4c rt_sweep_thread(const RtParams& P, int c, int k, int pg, int PG, c
   const bool packed_first = (k == 0);
   const float m = packed_first ? 0.0f : 1.0f;
   float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-  int p = pg;
-  if (p == 0 && p < P.P) {          // partition 0: the spectrum of the open block, from shared memory
-    const float4c h = ld_pair(Hk);
-    const float2 xa = xnew[k], xb = xnew[k + 1];
-    a0.x = fmaf(-m * h.a.y, xa.y, h.a.x * xa.x);
-    a0.y = packed_first ? h.a.y * xa.y : fmaf(h.a.y, xa.x, h.a.x * xa.y);
-    a1.x = fmaf(-h.b.y, xb.y, h.b.x * xb.x);
-    a1.y = fmaf(h.b.y, xb.x, h.b.x * xb.y);
-    p += PG;
-  }
-  for (; p + 3 * PG < P.P; p += 4 * PG) {       // 8 independent 16-byte loads in flight
-    float4c h[4], x[4];
+  // batches of 8 partitions: 16 independent 16-byte loads in flight per thread before any arithmetic (one SM only
+  // reaches its share of the L2 bandwidth with deep memory-level parallelism); the ragged last batch is predicated,
+  // partition 0 takes the spectrum of the open block from shared memory
+  for (int p = pg; p < P.P; p += 8 * PG) {
+    float4c h[8], x[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      h[u] = ld_pair(Hk + (long long)(p + u * PG) * P.M);
-      x[u] = ld_pair(Xk - (long long)(p + u * PG) * P.M);
+    for (int u = 0; u < 8; ++u) {
+      const int pp = p + u * PG;
+      if (pp < P.P) {
+        h[u] = ld_pair(Hk + (long long)pp * P.M);
+        if (pp == 0) { x[u].a = xnew[k]; x[u].b = xnew[k + 1]; }
+        else x[u] = ld_pair(Xk - (long long)pp * P.M);
+      } else {
+        h[u].a = h[u].b = x[u].a = x[u].b = make_float2(0.f, 0.f);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       float re = fmaf(h[u].a.x, x[u].a.x, a0.x);
       re = fmaf(-m * h[u].a.y, x[u].a.y, re);
       const float im = packed_first ? fmaf(h[u].a.y, x[u].a.y, a0.y) : fmaf(h[u].a.y, x[u].a.x, fmaf(h[u].a.x, x[u].a.y, a0.y));
@@ -146,16 +148,6 @@ PC_HD float4c rt_sweep_thread(const RtParams& P, int c, int k, int pg, int PG, c
       a1.x = fmaf(-h[u].b.y, x[u].b.y, fmaf(h[u].b.x, x[u].b.x, a1.x));
       a1.y = fmaf(h[u].b.y, x[u].b.x, fmaf(h[u].b.x, x[u].b.y, a1.y));
     }
-  }
-  for (; p < P.P; p += PG) {
-    const float4c h = ld_pair(Hk + (long long)p * P.M);
-    const float4c x = ld_pair(Xk - (long long)p * P.M);
-    float re = fmaf(h.a.x, x.a.x, a0.x);
-    re = fmaf(-m * h.a.y, x.a.y, re);
-    const float im = packed_first ? fmaf(h.a.y, x.a.y, a0.y) : fmaf(h.a.y, x.a.x, fmaf(h.a.x, x.a.y, a0.y));
-    a0 = make_float2(re, im);
-    a1.x = fmaf(-h.b.y, x.b.y, fmaf(h.b.x, x.b.x, a1.x));
-    a1.y = fmaf(h.b.y, x.b.x, fmaf(h.b.x, x.b.y, a1.y));
   }
   float4c r; r.a = a0; r.b = a1;
   return r;
@@ -313,6 +305,15 @@ __global__ void __launch_bounds__(256) k_rt_block(RtParams P) {
       }
     }
   }
+  if (P.done_flag) {
+    // every CTA that wrote output makes its stores visible system-wide, the cluster meets, CTA 0 raises the flag
+    __threadfence_system();
+    rt_cluster_sync();
+    if (rank == 0 && tid == 0) {
+      *reinterpret_cast<volatile unsigned int*>(P.done_flag) = P.done_val;
+      __threadfence_system();
+    }
+  }
 }
 #else
 // CPU emulation (tests/emu): the CTAs of the cluster run phase by phase; a DSMEM store is a store into the other
@@ -413,6 +414,7 @@ inline void emu_rt_block(const RtParams& P) {
         }
         P.out[(long long)o * P.out_stride + i] = acc;
       }
+  if (P.done_flag) *P.done_flag = P.done_val;
   for (int r = 0; r < n; ++r) {
     delete[] ct[r].bufA; delete[] ct[r].bufB; delete[] ct[r].xnew; delete[] ct[r].yfull;
     delete[] ct[r].xs; delete[] ct[r].ys; delete[] ct[r].mix; delete[] ct[r].red;

@@ -140,6 +140,28 @@ int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user);
  * Limits: C <= 8, n_in <= 8, n_out <= 8; not combinable with the slot exchange. */
 int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, const float* mix);
 
+/* The per-sample chain REEV-R runs on the host around the convolver (SURVEY 8f-4 and the rest of 8f-1), on the device:
+ *   send: dry * ysend -> low cut (HP) if lowcut_hz > 20 -> high cut (LP) if highcut_hz < 20000 -> predelay ring
+ *         (src/PluginProcessor.cpp:1639-1653, 1766-1790; filters = src/dsp/Filter.cpp state-variable sections, slope
+ *         0/1/2 = 6/12/24 dB, coefficients as Filter::init / getCoeff compute them);
+ *   convolvers LL, RR[, LR, RL] on the chain's L / R (a C = 2 or C = 4 handle);
+ *   wet:  L = LL (+ RL), R = RR (+ LR when true_stereo) ; * yrev ; mid/side width ; out = drygain * dry + wetgain * wet
+ *         (src/PluginProcessor.cpp:1832-1876).
+ * dry[2] / out[2]: host L, R; ysend / yrev: per-sample send and reverb envelopes (NULL = 1).  One H2D of the dry
+ * signal + envelopes and one D2H of the final mix per call, whatever the number of convolvers.
+ * b200conv_chain_configure(h, cfg) after the IR is loaded (resets filter states and the delay line; NULL disables). */
+typedef struct b200conv_chain_config {
+  double srate;
+  float lowcut_hz;  int lowcut_slope;
+  float highcut_hz; int highcut_slope;
+  int predelay;                 /* samples */
+  float width, drygain, wetgain;
+  int true_stereo;              /* quad handles: add RL to the left and LR to the right */
+} b200conv_chain_config;
+int b200conv_chain_configure(b200conv_t* h, const b200conv_chain_config* cfg);
+int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* ysend, const float* yrev,
+                           float* const* out, size_t len);
+
 /* IR hot-swap helpers (the reference replays a 0.25 s "warmer" ring through the freshly
  * loaded convolver call by call and crossfades two convolvers on the host for 50 ms,
  * src/PluginProcessor.cpp:1695-1750,1800-1830).

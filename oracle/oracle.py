@@ -36,7 +36,8 @@ def _needs_build(so: str, src: str) -> bool:
 
 
 def _load_oracle() -> C.CDLL:
-    if _needs_build(_ORACLE_SO, os.path.join(_HERE, "partconv_oracle.c")):
+    if _needs_build(_ORACLE_SO, os.path.join(_HERE, "partconv_oracle.c")) or \
+            _needs_build(_ORACLE_SO, os.path.join(_HERE, "chain_oracle.c")):
         build()
     lib = C.CDLL(_ORACLE_SO)
     for kind in ("uniform", "twostage"):
@@ -62,6 +63,18 @@ def _load_oracle() -> C.CDLL:
     lib.oc_apply_decay.argtypes = [_f32p, C.c_size_t, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.c_double]
     lib.oc_decay_window.restype = None
     lib.oc_decay_window.argtypes = [_f32p]
+    # send / wet chain (chain_oracle.c)
+    lib.oc_filter_create.restype = C.c_void_p
+    lib.oc_filter_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    lib.oc_filter_destroy.argtypes = [C.c_void_p]
+    lib.oc_filter_run.argtypes = [C.c_void_p, _f32p, _f32p, C.c_size_t]
+    lib.oc_filter_coeff.restype = C.c_float
+    lib.oc_filter_coeff.argtypes = [C.c_float, C.c_float]
+    lib.oc_chain_create.restype = C.c_void_p
+    lib.oc_chain_create.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    lib.oc_chain_destroy.argtypes = [C.c_void_p]
+    lib.oc_chain_send.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_size_t]
+    lib.oc_chain_wet.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, _f32p, _f32p, _f32p, C.c_size_t]
     lib.oc_uniform_partitions.restype = C.c_size_t
     lib.oc_uniform_partitions.argtypes = [C.c_void_p]
     lib.oc_uniform_block.restype = C.c_size_t
@@ -201,6 +214,112 @@ class RefUniform(OracleUniform):
 class RefTwoStage(OracleTwoStage):
     """The unmodified reference TwoStageFFTConvolver (oracle/_ref)."""
     _which = "ref"
+
+
+_REF_FILTER_SO = os.path.join(_HERE, "_ref", "libreffilter.so")
+
+
+def ref_filter_available() -> bool:
+    if os.path.exists(_REF_FILTER_SO):
+        return True
+    if os.path.isdir("/root/reference/src/dsp"):
+        build()
+        return os.path.exists(_REF_FILTER_SO)
+    return False
+
+
+class OracleFilter:
+    """C restatement of REEV-R's Filter (src/dsp/Filter.cpp): slope 0/1/2 = 6/12/24 dB, mode 0/1/2 = LP/BP/HP."""
+
+    def __init__(self, slope: int, mode: int, srate: float, freq: float, q: float):
+        self._l = _lib("oc")
+        self._h = self._l.oc_filter_create(slope, mode, srate, freq, q)
+
+    def run(self, x) -> np.ndarray:
+        x = _as_f32(x)
+        y = np.empty_like(x)
+        self._l.oc_filter_run(self._h, x, y, x.size)
+        return y
+
+    def __del__(self):
+        try:
+            self._l.oc_filter_destroy(self._h)
+        except Exception:
+            pass
+
+
+class RefFilter:
+    """The unmodified reference Filter (oracle/_ref/libreffilter.so)."""
+
+    def __init__(self, slope: int, mode: int, srate: float, freq: float, q: float):
+        if "reffilter" not in _libs:
+            if not ref_filter_available():
+                raise RuntimeError("oracle/_ref/libreffilter.so not built and /root/reference absent")
+            l = C.CDLL(_REF_FILTER_SO)
+            l.ref_filter_create.restype = C.c_void_p
+            l.ref_filter_create.argtypes = [C.c_int, C.c_int]
+            l.ref_filter_destroy.argtypes = [C.c_void_p]
+            l.ref_filter_init.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+            l.ref_filter_reset.argtypes = [C.c_void_p, C.c_float]
+            l.ref_filter_run.argtypes = [C.c_void_p, _f32p, _f32p, C.c_size_t]
+            l.ref_filter_coeff.restype = C.c_float
+            l.ref_filter_coeff.argtypes = [C.c_float, C.c_float]
+            _libs["reffilter"] = l
+        self._l = _libs["reffilter"]
+        self._h = self._l.ref_filter_create(slope, mode)
+        self._l.ref_filter_init(self._h, srate, freq, q)
+        self._l.ref_filter_reset(self._h, 0.0)
+
+    def run(self, x) -> np.ndarray:
+        x = _as_f32(x)
+        y = np.empty_like(x)
+        self._l.ref_filter_run(self._h, x, y, x.size)
+        return y
+
+    def __del__(self):
+        try:
+            self._l.ref_filter_destroy(self._h)
+        except Exception:
+            pass
+
+
+def filter_coeff(freq: float, srate: float, ref: bool = False) -> float:
+    if ref:
+        RefFilter(0, 0, srate, freq, 0.5)          # loads the library
+        return float(_libs["reffilter"].ref_filter_coeff(freq, srate))
+    return float(_lib("oc").oc_filter_coeff(freq, srate))
+
+
+class OracleChain:
+    """C restatement of the send / wet chain of processBlock (src/PluginProcessor.cpp:1639-1653, 1766-1790, 1832-1876)."""
+
+    def __init__(self, srate, lowcut_hz, lowcut_slope, highcut_hz, highcut_slope, predelay, width, drygain, wetgain,
+                 delay_size: int = 0):
+        self._l = _lib("oc")
+        self._h = self._l.oc_chain_create(srate, lowcut_hz, lowcut_slope, highcut_hz, highcut_slope, predelay,
+                                          delay_size or max(2 * predelay, 1), width, drygain, wetgain)
+
+    def send(self, dryL, dryR, ysend):
+        dryL, dryR, ysend = _as_f32(dryL), _as_f32(dryR), _as_f32(ysend)
+        a, b = np.empty_like(dryL), np.empty_like(dryR)
+        self._l.oc_chain_send(self._h, dryL, dryR, ysend, a, b, dryL.size)
+        return a, b
+
+    def wet(self, dryL, dryR, LL, RR, LR, RL, yrev):
+        arrs = [_as_f32(v) for v in (dryL, dryR, LL, RR)]
+        lr = _as_f32(LR) if LR is not None else None
+        rl = _as_f32(RL) if RL is not None else None
+        yrev = _as_f32(yrev)
+        oL, oR = np.empty_like(arrs[0]), np.empty_like(arrs[1])
+        self._l.oc_chain_wet(self._h, *arrs, lr.ctypes.data if lr is not None else None,
+                             rl.ctypes.data if rl is not None else None, yrev, oL, oR, arrs[0].size)
+        return oL, oR
+
+    def __del__(self):
+        try:
+            self._l.oc_chain_destroy(self._h)
+        except Exception:
+            pass
 
 
 def apply_decay(ir, lut, srate: float) -> np.ndarray:

@@ -25,6 +25,12 @@ class Config(C.Structure):
     ]
 
 
+class ChainConfig(C.Structure):
+    _fields_ = [("srate", C.c_double), ("lowcut_hz", C.c_float), ("lowcut_slope", C.c_int), ("highcut_hz", C.c_float),
+                ("highcut_slope", C.c_int), ("predelay", C.c_int), ("width", C.c_float), ("drygain", C.c_float),
+                ("wetgain", C.c_float), ("true_stereo", C.c_int)]
+
+
 class StageInfo(C.Structure):
     _fields_ = [
         ("block", C.c_size_t),
@@ -75,6 +81,8 @@ SYMBOLS = [
                                                   C.c_int, C.c_int, C.c_int]),
     ("b200conv_register_host", C.c_int, [C.c_void_p, C.c_size_t]),
     ("b200conv_unregister_host", C.c_int, [C.c_void_p]),
+    ("b200conv_chain_configure", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("b200conv_chain_process", C.c_int, [C.c_void_p, _PP, C.c_void_p, C.c_void_p, _PP, C.c_size_t]),
     ("b200conv_alloc_host", C.c_void_p, [C.c_size_t]),
     ("b200conv_free_host", None, [C.c_void_p]),
     ("b200conv_version", C.c_char_p, []),

@@ -127,6 +127,26 @@ class Engine:
         self._check(self._l.b200conv_process_device_sliced(self._h, in_ptr, in_stride, out_ptr, out_stride, n,
                                                            slice_rank, slice_count, int(sync)), "process_device_sliced")
 
+    def chain_configure(self, srate: float, lowcut_hz: float = 20.0, lowcut_slope: int = 0, highcut_hz: float = 20000.0,
+                        highcut_slope: int = 0, predelay: int = 0, width: float = 1.0, drygain: float = 1.0,
+                        wetgain: float = 1.0, true_stereo: bool = True) -> None:
+        """The send / wet chain of REEVRAudioProcessor::processBlock on the device (b200conv_chain_configure)."""
+        cfg = _lib.ChainConfig(srate, lowcut_hz, lowcut_slope, highcut_hz, highcut_slope, predelay, width, drygain, wetgain,
+                               int(true_stereo))
+        self._check(self._l.b200conv_chain_configure(self._h, C.byref(cfg)), "chain_configure")
+
+    def chain_process(self, dryL, dryR, ysend=None, yrev=None):
+        """(outL, outR) = drygain * dry + wetgain * width(yrev * mixdown(convolvers(predelay(filters(dry * ysend)))))"""
+        xs = [np.ascontiguousarray(a, dtype=np.float32) for a in (dryL, dryR)]
+        n = xs[0].size
+        env = [None if e is None else np.ascontiguousarray(e, dtype=np.float32) for e in (ysend, yrev)]
+        ys = [np.empty(max(n, 1), np.float32)[:n] for _ in range(2)]
+        if n:
+            self._check(self._l.b200conv_chain_process(
+                self._h, _ptr_array(xs), env[0].ctypes.data if env[0] is not None else None,
+                env[1].ctypes.data if env[1] is not None else None, _ptr_array(ys), n), "chain_process")
+        return ys[0], ys[1]
+
     def clear(self):
         self._check(self._l.b200conv_clear(self._h), "clear")
 

@@ -42,6 +42,7 @@
 #include "kernels_stream.cuh"
 #include "kernels_fft512.cuh"
 #include "kernels_rt.cuh"
+#include "kernels_chain.cuh"
 
 namespace {
 
@@ -139,6 +140,18 @@ struct b200conv {
   // time-slice sharding: Y row 0 (the overlap state, spectrum of the last completed block) does not belong to
   // the block in front of the open one any more (the timeline was advanced by forward FFTs only)
   bool yprev_stale = false;
+  // send / wet chain around the convolver (b200conv_chain_*, kernels_chain.cuh)
+  bool chain_on = false;
+  bool route_in_only = false;        // chain calls: convolver c reads chain input c & 1, outputs stay per convolver
+  b200conv_chain_config chain_cfg{};
+  pc::ChainFilter chain_lc{}, chain_hc{};
+  float* c_io = nullptr;             // [dry L, dry R, ysend, yrev, out L, out R][Lmax] staging
+  float* c_conv_in = nullptr;        // [2][Lmax] convolver input (after filters + predelay)
+  float* c_filt = nullptr;           // [2][Lmax]
+  float* c_state = nullptr;          // [2][8] filter states
+  float* c_ring = nullptr;           // [2][ring] predelay ring
+  size_t c_ring_size = 0;
+  long long c_ring_pos = 0;
   // tuning / A-B switches (b200conv_set_option; defaults from the environment)
   bool opt_rt = std::getenv("B200CONV_NO_RT") == nullptr;
   bool opt_fft512 = std::getenv("B200CONV_NO_FFT512") == nullptr;
@@ -237,6 +250,10 @@ void free_all(b200conv* h) {
     h->din[i] = h->dout[i] = nullptr;
   }
   cudaFree(h->dch[0]); h->dch[0] = nullptr;
+  cudaFree(h->c_io); cudaFree(h->c_conv_in); cudaFree(h->c_filt); cudaFree(h->c_state); cudaFree(h->c_ring);
+  h->c_io = h->c_conv_in = h->c_filt = h->c_state = h->c_ring = nullptr;
+  h->c_ring_size = 0; h->c_ring_pos = 0;
+  h->chain_on = false; h->route_in_only = false;
   if (h->hpin_in) cudaFreeHost(h->hpin_in);
   if (h->hpin_out) cudaFreeHost(h->hpin_out);
   if (h->hflag) cudaFreeHost(h->hflag);
@@ -873,7 +890,7 @@ int init_common(b200conv* h, int n_stages, const size_t* blocks, const size_t* o
 // C plain channels) into a C-channel staging buffer
 int copy_in(b200conv* h, float* dst, size_t dstride, const float* src, size_t sstride, size_t count) {
   if (count == 0) return 0;
-  if (!h->route_on) {
+  if (!h->route_on && !h->route_in_only) {
     CU_CHECK(h, cudaMemcpy2DAsync(dst, dstride * sizeof(float), src, sstride * sizeof(float), count * sizeof(float), h->C,
                                   cudaMemcpyDeviceToDevice, h->s_main));
   } else {
@@ -885,7 +902,7 @@ int copy_in(b200conv* h, float* dst, size_t dstride, const float* src, size_t ss
 }
 
 void set_cmap(const b200conv* h, pc::FwdParams& fp, bool direct) {
-  fp.use_cmap = (direct && h->route_on) ? 1 : 0;
+  fp.use_cmap = (direct && (h->route_on || h->route_in_only)) ? 1 : 0;
   for (int c = 0; c < 8; ++c) fp.cmap[c] = h->in_map[c];
 }
 
@@ -1427,7 +1444,7 @@ int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, 
   P.M = M; P.C = C; P.NC = nc; P.P = s0.P;
   P.fill = s0.fill; P.len = (int)len; P.complete = (s0.fill + (int)len == M) ? 1 : 0;
   P.in = in; P.in_stride = (long long)in_stride;
-  for (int c = 0; c < 8; ++c) P.in_map[c] = h->route_on ? h->in_map[c] : c;
+  for (int c = 0; c < 8; ++c) P.in_map[c] = (h->route_on || h->route_in_only) ? h->in_map[c] : c;
   if (C > 8) return fail(h, B200CONV_ESTATE, "real-time kernel supports up to 8 convolvers per handle");
   P.inbuf0 = s0.inbuf; P.inbuf0_stride = (long long)s0.in_stride;
   P.H = s0.H; P.h_cstride = (long long)s0.Prows * M;
@@ -1994,10 +2011,167 @@ int b200conv_process_xfade(b200conv_t* ho, b200conv_t* hn, const float* const* i
   return B200CONV_OK;
 }
 
+// ---- send / wet chain (SURVEY 8f-4 + the rest of 8f-1) ------------------------------------------------------------
+namespace {
+// Filter::getCoeff (src/dsp/Filter.h:40-44): tan() through the reference's 2048-point lookup table with its cubic
+// interpolation (src/dsp/Filter.h:28-36, src/dsp/Utils.h:50-112) — the coefficient has to be the reference's, bit for bit
+float chain_coeff(float freq, float srate) {
+  static float lut[2048];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const float pi = 3.14159265358979323846f;
+    for (int i = 0; i < 2048; ++i) {
+      const float x = (float)i / 2047.0f;
+      float mapped = 0.0f + x * (0.5f - 0.0f);
+      mapped = std::min(std::max(mapped, 0.0f), 0.5f);
+      const float max_rads = 0.499f * pi, scaled = mapped * pi;
+      lut[i] = std::tan(std::min(max_rads, scaled));
+    }
+  });
+  freq = std::min(std::max(freq, 20.0f), srate * 0.48f);
+  float ratio = std::min(std::max(freq / srate, 0.0f), 0.5f);
+  const float scaler = 2047.0f / 0.5f;
+  const float index = ratio * scaler + 0.0f;
+  const int i = (int)index;
+  const float t = index - (float)i;
+  const int i0 = std::max(0, i - 1), i1 = i, i2 = std::min(2047, i + 1), i3 = std::min(2047, i + 2);
+  const float y0 = lut[i0], y1 = lut[i1], y2 = lut[i2], y3 = lut[i3];
+  const float a0 = y3 - y2 - y0 + y1, a1 = y0 - y1 - a0, a2 = y2 - y0, a3 = y1;
+  return (a0 * t * t * t) + (a1 * t * t) + (a2 * t) + a3;
+}
+
+// Filter::init (src/dsp/Filter.cpp:3-21) with the q the processor passes (src/PluginProcessor.cpp:845-848)
+pc::ChainFilter chain_filter(bool on, int slope, int mode, float srate, float freq) {
+  pc::ChainFilter f{};
+  f.on = on ? 1 : 0; f.slope = slope; f.mode = mode;
+  const float q = slope == 2 ? 0.0765f : 0.2929f, q2 = 0.6173f;
+  f.g = chain_coeff(freq, srate);
+  f.k = 2 - 2 * q;
+  f.k2 = 2 - 2 * q2;
+  if (slope == 0) {
+    f.g = f.g / (1.0f + f.g);
+  } else {
+    f.a1 = 1.0f / (1.0f + f.g * (f.g + f.k));
+    f.a2 = f.g * f.a1;
+    f.a3 = f.g * f.a2;
+    f.a12 = 1.0f / (1.0f + f.g * (f.g + f.k2));
+    f.a22 = f.g * f.a12;
+    f.a32 = f.g * f.a22;
+  }
+  return f;
+}
+}  // namespace
+
+int b200conv_chain_configure(b200conv_t* h, const b200conv_chain_config* cfg) {
+  REQUIRE_CUDA(h);
+  if (!cfg) { h->chain_on = false; h->route_in_only = false; return B200CONV_OK; }
+  if (h->C != 2 && h->C != 4) return fail(h, B200CONV_ESTATE, "the send / wet chain needs a stereo (C = 2) or quad (C = 4) handle");
+  if (h->route_on) return fail(h, B200CONV_ESTATE, "the send / wet chain cannot be combined with b200conv_set_routing");
+  if (h->cfg.shard_count != 1) return fail(h, B200CONV_ESTATE, "the send / wet chain needs an unsharded handle");
+  if (h->stages.empty()) return fail(h, B200CONV_ESTATE, "load an impulse response first");
+  if (cfg->srate <= 0 || cfg->predelay < 0 || cfg->lowcut_slope < 0 || cfg->lowcut_slope > 2 || cfg->highcut_slope < 0 || cfg->highcut_slope > 2)
+    return fail(h, B200CONV_EINVAL, "bad chain configuration");
+  if (int rc = set_device(h)) return rc;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  h->chain_cfg = *cfg;
+  const float sr = (float)cfg->srate;
+  h->chain_lc = chain_filter(cfg->lowcut_hz > 20.0f, cfg->lowcut_slope, 2, sr, cfg->lowcut_hz);          // HP, PluginProcessor.cpp:1643
+  h->chain_hc = chain_filter(cfg->highcut_hz < 20000.0f, cfg->highcut_slope, 0, sr, cfg->highcut_hz);   // LP, :1647
+  const size_t L = h->Lmax;
+  const size_t ring = next_pow2((size_t)cfg->predelay + L + 1);
+  if (!h->c_io) {
+    CU_CHECK(h, cudaMalloc(&h->c_io, 6 * L * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&h->c_conv_in, 2 * L * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&h->c_filt, 2 * L * sizeof(float)));
+    CU_CHECK(h, cudaMalloc(&h->c_state, 2 * pc::kChainStates * sizeof(float)));
+  }
+  if (ring != h->c_ring_size) {
+    cudaFree(h->c_ring); h->c_ring = nullptr;
+    CU_CHECK(h, cudaMalloc(&h->c_ring, 2 * ring * sizeof(float)));
+    h->c_ring_size = ring;
+  }
+  // Filter::reset(0) + cleared delay line (src/PluginProcessor.cpp:654-657)
+  CU_CHECK(h, cudaMemsetAsync(h->c_state, 0, 2 * pc::kChainStates * sizeof(float), h->s_main));
+  CU_CHECK(h, cudaMemsetAsync(h->c_ring, 0, 2 * ring * sizeof(float), h->s_main));
+  h->c_ring_pos = 0;
+  for (int c = 0; c < 8; ++c) h->in_map[c] = c & 1;        // LL, RR, LR, RL <- L, R, L, R (StereoConvolver.cpp:35-40)
+  h->chain_on = true;
+  CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+  return B200CONV_OK;
+}
+
+int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* ysend, const float* yrev, float* const* out, size_t len) {
+  REQUIRE_CUDA(h);
+  if (len == 0) return B200CONV_OK;
+  if (!h->chain_on) return fail(h, B200CONV_ESTATE, "b200conv_chain_configure first");
+  if (!dry || !out || !dry[0] || !dry[1] || !out[0] || !out[1]) return fail(h, B200CONV_EINVAL, "null buffer");
+  if (h->stages.empty()) return fail(h, B200CONV_ESTATE, "no impulse response loaded");
+  if (int rc = set_device(h)) return rc;
+  const int C = h->C;
+  const size_t L = h->Lmax, B0 = h->stages[0].B;
+  const size_t chunk = L - B0;
+  float* d_dry = h->c_io; float* d_send = h->c_io + 2 * L; float* d_rev = h->c_io + 3 * L; float* d_out = h->c_io + 4 * L;
+  for (size_t done = 0; done < len;) {
+    const size_t n = std::min(len - done, chunk);
+    for (int ch = 0; ch < 2; ++ch)
+      CU_CHECK(h, cudaMemcpyAsync(d_dry + ch * L, dry[ch] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    if (ysend) CU_CHECK(h, cudaMemcpyAsync(d_send, ysend + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    if (yrev) CU_CHECK(h, cudaMemcpyAsync(d_rev, yrev + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    pc::ChainSendParams sp{};
+    sp.dry = d_dry; sp.dry_stride = (long long)L; sp.ysend = ysend ? d_send : nullptr;
+    sp.conv_in = h->c_conv_in; sp.conv_stride = (long long)L;
+    sp.filt = h->c_filt; sp.filt_stride = (long long)L;
+    sp.state = h->c_state;
+    sp.ring = h->c_ring; sp.ring_stride = (long long)h->c_ring_size; sp.ring_mask = (long long)h->c_ring_size - 1;
+    sp.ring_pos = h->c_ring_pos; sp.predelay = h->chain_cfg.predelay; sp.n = (long long)n;
+    sp.lc = h->chain_lc; sp.hc = h->chain_hc;
+    const int T = n <= 4096 ? 64 : 1024;
+#if defined(PC_EMULATE)
+    pc::emu_chain_send(sp, T);
+#else
+    pc::k_chain_send<<<2, T, 0, h->s_main>>>(sp);
+    CU_CHECK(h, cudaGetLastError());
+#endif
+    h->launches++;
+    h->c_ring_pos = (h->c_ring_pos + (long long)n) & ((long long)h->c_ring_size - 1);
+    // the convolvers: LL, RR[, LR, RL] read the chain's L / R, per-convolver outputs stay on the device
+    h->route_in_only = true;
+    int rc = 0;
+    if (const int nc = rt_cluster_ctas(h, n)) rc = rt_call(h, nc, h->c_conv_in, L, h->dch[0], L, n, false);
+    else rc = run_group(h, h->c_conv_in, L, h->dch[0], L, n, false);
+    h->route_in_only = false;
+    if (rc) return rc;
+    pc::ChainWetParams wp{};
+    wp.dry = d_dry; wp.dry_stride = (long long)L;
+    wp.conv = h->dch[0]; wp.conv_stride = (long long)L;
+    wp.yrev = yrev ? d_rev : nullptr;
+    wp.out = d_out; wp.out_stride = (long long)L; wp.n = (long long)n;
+    wp.quad_ts = (C == 4 && h->chain_cfg.true_stereo) ? 1 : 0;
+    wp.width = h->chain_cfg.width; wp.drygain = h->chain_cfg.drygain; wp.wetgain = h->chain_cfg.wetgain;
+#if defined(PC_EMULATE)
+    pc::emu_chain_wet(wp);
+#else
+    pc::k_chain_wet<<<(unsigned)((n + 255) / 256), 256, 0, h->s_main>>>(wp);
+    CU_CHECK(h, cudaGetLastError());
+#endif
+    h->launches++;
+    for (int ch = 0; ch < 2; ++ch)
+      CU_CHECK(h, cudaMemcpyAsync(out[ch] + done, d_out + ch * L, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    done += n;
+  }
+  return B200CONV_OK;
+}
+
 int b200conv_clear(b200conv_t* h) {
   REQUIRE_CUDA(h);
   if (int rc = set_device(h)) return rc;
   if (int rc = clear_state(h)) return rc;
+  if (h->chain_on) {            // the chain's own history goes with the convolver's
+    CU_CHECK(h, cudaMemsetAsync(h->c_state, 0, 2 * pc::kChainStates * sizeof(float), h->s_main));
+    CU_CHECK(h, cudaMemsetAsync(h->c_ring, 0, 2 * h->c_ring_size * sizeof(float), h->s_main));
+    h->c_ring_pos = 0;
+  }
   CU_CHECK(h, cudaStreamSynchronize(h->s_main));
   return p2p_check(h);
 }
@@ -2064,6 +2238,7 @@ int b200conv_set_reduce(b200conv_t* h, b200conv_reduce_fn fn, void* user) {
 int b200conv_set_routing(b200conv_t* h, int n_in, const int* in_map, int n_out, const float* mix) {
   if (!h) return B200CONV_EINVAL;
   if (n_in == 0) { h->route_on = false; return B200CONV_OK; }
+  if (h->chain_on) return fail(h, B200CONV_ESTATE, "routing cannot be combined with the send / wet chain");
   const int C = h->C;
   if (C > 8 || n_in < 1 || n_in > C || n_out < 1 || n_out > C || !in_map || !mix)
     return fail(h, B200CONV_EINVAL, "routing needs C <= 8, 1 <= n_in, n_out <= C, in_map[C] and mix[n_out*C]");

@@ -332,6 +332,18 @@ def apply_decay(ir, lut, srate: float) -> np.ndarray:
     return buf
 
 
+def ref_apply_decay(ir, lut, srate: float) -> np.ndarray:
+    """The same STFT loop driven through the reference's own compiled AudioFFT (oracle/ref_shim.cpp::ref_stft_decay)."""
+    lib = _lib("ref")
+    lib.ref_stft_decay.restype = None
+    lib.ref_stft_decay.argtypes = [_f32p, C.c_size_t, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.c_double, _f32p]
+    buf = np.array(ir, dtype=np.float32, copy=True)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    if buf.size:
+        lib.ref_stft_decay(buf, buf.size, lut, float(srate), decay_window())
+    return buf
+
+
 def decay_window() -> np.ndarray:
     w = np.empty(4096, np.float32)
     _lib("oc").oc_decay_window(w)

@@ -116,22 +116,32 @@ PC_HD int f512_s2(int k2, int q0, int n0) { return k2 * 64 + ((q0 ^ (k2 & 1)) <<
 // ---------------------------------------------------------------------------------------------------------
 // forward: z[n] = (x[2n], x[2n+1]), n < 256 valid (the upper half of [x ; 0] is zero)
 // ---------------------------------------------------------------------------------------------------------
-// step 1: loads + DFT8 over n2 + twiddle, result into the exchange buffer (layout s1)
-PC_HD void f512_fwd_p1(int lane, const float* src, int nv, bool vec, float2* S, const float2* tab) {
+// loads of step 1: the 8 non-zero points of the lane's two columns (z[64 n2 + m], n2 < 4), a[4 h + n2]
+PC_HD void f512_fwd_load(int lane, const float* src, int nv, bool vec, float2* a) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = lane + 32 * h;
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+      const int n = 64 * n2 + m;
+      if (vec) {
+        a[4 * h + n2] = *reinterpret_cast<const float2*>(src + 2 * n);
+      } else {
+        const int i0 = 2 * n, i1 = i0 + 1;
+        a[4 * h + n2] = make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
+      }
+    }
+  }
+}
+
+// step 1: DFT8 over n2 (upper half of the input is the zero padding) + twiddle, result into the exchange buffer (layout s1)
+PC_HD void f512_fwd_p1(int lane, const float2* in, float2* S, const float2* tab) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int m = lane + 32 * h;
     float2 a[8];
 #pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) {
-      const int n = 64 * n2 + m;
-      if (vec) {
-        a[n2] = *reinterpret_cast<const float2*>(src + 2 * n);
-      } else {
-        const int i0 = 2 * n, i1 = i0 + 1;
-        a[n2] = make_float2(i0 < nv ? src[i0] : 0.0f, i1 < nv ? src[i1] : 0.0f);
-      }
-    }
+    for (int n2 = 0; n2 < 4; ++n2) a[n2] = in[4 * h + n2];
 #pragma unroll
     for (int n2 = 4; n2 < 8; ++n2) a[n2] = make_float2(0.0f, 0.0f);
     f512_dft8<false>(a);
@@ -309,12 +319,24 @@ __global__ void __launch_bounds__(256, 4) k_fwd_fft512(FwdParams P, const float2
   const int c = blockIdx.y;
   const long long nv_total = P.nvalid_c ? (long long)P.nvalid_c[c] : P.nvalid;
   const float* src_c = P.src + (long long)(P.use_cmap ? P.cmap[c] : c) * P.src_cstride;
-  for (int blk = blockIdx.x * 8 + threadIdx.y; blk < P.nblocks; blk += gridDim.x * 8) {
+  // software pipeline: the loads of the warp's NEXT block are issued before the current one is transformed
+  auto issue = [&](int blk, float2* a) {
     const long long rem = nv_total - (long long)blk * kF512_M;
     const int nv = rem <= 0 ? 0 : (rem > kF512_M ? kF512_M : (int)rem);
     const float* src = src_c + (long long)blk * kF512_M;
     const bool vec = nv == kF512_M && (reinterpret_cast<size_t>(src) & 7) == 0;
-    f512_fwd_p1(lane, src, nv, vec, S, tab);
+    f512_fwd_load(lane, src, nv, vec, a);
+  };
+  const int stride = gridDim.x * 8;
+  int blk = blockIdx.x * 8 + threadIdx.y;
+  float2 nxt[8];
+  if (blk < P.nblocks) issue(blk, nxt);
+  for (; blk < P.nblocks; blk += stride) {
+    float2 cur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    if (blk + stride < P.nblocks) issue(blk + stride, nxt);
+    f512_fwd_p1(lane, cur, S, tab);
     __syncwarp();
     float2 A[8], B[8];
     f512_mid_load<false>(lane, S, tab, A, B);
@@ -371,7 +393,11 @@ inline void emu_fwd_fft512(int nblocks, int C, const FwdParams& P, const float2*
       const long long rem = nv_total - (long long)blk * kF512_M;
       const int nv = rem <= 0 ? 0 : (rem > kF512_M ? kF512_M : (int)rem);
       const float* src = src_c + (long long)blk * kF512_M;
-      for (int l = 0; l < 32; ++l) f512_fwd_p1(l, src, nv, false, S, tab);
+      for (int l = 0; l < 32; ++l) {
+        float2 a[8];
+        f512_fwd_load(l, src, nv, false, a);
+        f512_fwd_p1(l, a, S, tab);
+      }
       for (int l = 0; l < 32; ++l) f512_mid_load<false>(l, S, tab, A[l], B[l]);
       for (int l = 0; l < 32; ++l) f512_mid_store<false>(l, S, A[l], B[l]);
       for (int l = 0; l < 32; ++l) f512_fwd_p3(l, S, tab, P.dst + (long long)c * P.dst_cstride + (P.dst_row0 + blk) * (long long)kF512_M);

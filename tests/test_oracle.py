@@ -141,3 +141,15 @@ def test_apply_decay_restatement_properties():
     assert np.max(np.abs(got[64:1024] - want[64:1024])) <= 1e-4 * np.max(np.abs(want))
     assert np.max(np.abs(got[1024:] - want[1024:])) <= 1e-5 * np.max(np.abs(want))
     assert np.sum(got[-8000:] ** 2) < 0.2 * np.sum(h[-8000:] ** 2)      # the tail really decays faster
+
+
+@pytest.mark.skipif(not orc.ref_available(), reason="oracle/_ref not built and /root/reference absent")
+def test_apply_decay_restatement_pinned_by_the_reference_fft():
+    """oc_apply_decay (Impulse::applyDecay restated, own FFT) against the same STFT loop driven through the reference's
+    compiled audiofft::AudioFFT (oracle/ref_shim.cpp::ref_stft_decay): the (f3) oracle is no longer unpinned."""
+    for n in (30000, 5000, 4096, 1025, 100):
+        h = orc.synth_ir(n)
+        for lut in (np.ones(2049), np.linspace(1.0, 0.7, 2049), np.linspace(0.8, 1.05, 2049)):
+            a = orc.apply_decay(h, lut, 48000.0)
+            b = orc.ref_apply_decay(h, lut, 48000.0)
+            assert np.max(np.abs(a - b)) <= 1e-6 * max(np.max(np.abs(b)), 1e-30)

@@ -113,7 +113,10 @@ size_t b200conv_ir_len(const b200conv_t* h, int channel);    /* post-trim tap co
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 unsigned long long b200conv_launch_count(const b200conv_t* h);
 /* Tuning / A-B switches: "rt" (1 = real-time calls that stay inside the open block run as ONE cluster-kernel launch
- * with zero-copy I/O, 0 = multi-kernel path), "fft512" (1 = register-resident FFT kernels for block size 512). */
+ * with zero-copy I/O, 0 = multi-kernel path), "fft512" (1 = register-resident FFT kernels for block size 512),
+ * "slice_keep_tail" (default 1; 0 = b200conv_process_sliced does not upload / transform the last P blocks of the call:
+ * the handle then only supports a following sliced call whose slice starts >= P blocks into the call — every rank
+ * but 0 of a steady batch job — until the next b200conv_clear). */
 int    b200conv_set_option(b200conv_t* h, const char* name, int value);
 /* Device time (ms) spent in the dominant CMAC kernel / all kernels during the last
  * b200conv_process_device call, measured with CUDA events on the handle's stream
@@ -201,6 +204,29 @@ int    b200conv_p2p_set_host_barrier(b200conv_t* h, b200conv_barrier_fn fn, void
  * on the host from the EQ bands); srate as in the reference (sets the early-reflection blocks that are
  * left untouched).  Stand-alone call: no handle, own temporary device buffers. */
 int b200conv_ir_decay_eq(int device, float* ir, size_t n, const double* lut, double srate);
+
+/* SURVEY 8f-3, the pipeline: the device-resident subset of Impulse::recalcImpulse (src/dsp/Impulse.cpp:297-360) in the
+ * reference's order — auto gain (:313-320, :703-720), reverse (:322-330), trim (:437-470), gain (:472-486), decay EQ
+ * (:602-648), clip (:488-501), attack / decay envelope (:651-680) — on the raw taps of all 2 / 4 channels with ONE upload.
+ * (Resampling, stretch and the parametric EQ stay on the host.)
+ *   b200conv_ir_shape            shaped taps back to the host (out[c] needs room for n floats, *out_len taps written);
+ *   b200conv_init_*_shaped       shape on the device and build the partition spectra straight from the device-resident
+ *                                taps — the IR never returns to the host between shaping and FFTConvolver::init. */
+typedef struct b200conv_ir_shape_params {
+  int autogain, reverse;
+  float trim_left, trim_right;      /* fractions of the length removed at either end */
+  float gain;
+  const double* decay_lut;          /* 2049 per-bin decay factors (Impulse.cpp:566-590), NULL = no decay EQ */
+  double srate;
+  int clip;
+  float attack, decay;              /* fractions of the (trimmed) length */
+} b200conv_ir_shape_params;
+int b200conv_ir_shape(int device, const float* const* raw, int n_channels, size_t n, const b200conv_ir_shape_params* sp,
+                      float* const* out, size_t* out_len);
+int b200conv_init_uniform_shaped(b200conv_t* h, size_t block, const float* const* raw, size_t n,
+                                 const b200conv_ir_shape_params* sp);
+int b200conv_init_twostage_shaped(b200conv_t* h, size_t head_block, size_t tail_block, const float* const* raw, size_t n,
+                                  const b200conv_ir_shape_params* sp);
 
 /* Pinned host memory helpers (staging buffers for the e2e path).  register/unregister page-lock memory the caller
  * owns (e.g. a shared-memory region several per-GPU processes write their output slices into). */

@@ -206,3 +206,62 @@ void oc_chain_wet(void* p, const float* dryL, const float* dryR, const float* LL
     outR[i] = dryR[i] * c->drygain + rout * c->wetgain;
   }
 }
+
+/* ---- IR shaping pipeline: the device-resident subset of Impulse::recalcImpulse
+ *      (src/dsp/Impulse.cpp:297-360) in the reference's order:
+ *        calculateAutoGain :703-720 -> scale :313-320 ; reverse :322-330 ; applyTrim :437-470 ; applyGain :472-486 ;
+ *        applyDecayEQ -> applyDecay :602-648 (oc_apply_decay, pinned by the reference's AudioFFT) ; applyClip :488-501 ;
+ *        applyEnvelope :651-680.
+ *      Not covered (stay on the host, JUCE interpolators / other filter class): resampleIRToProjectRate, applyStretch,
+ *      applyParamEQ.  ch[c]: C channels of n taps, shaped in place; returns the new length (trim shortens). ---- */
+void oc_apply_decay(float* buf, size_t n, const double* lut, double srate);
+
+size_t oc_ir_shape(float** ch, int C, size_t n, int autogain, int reverse, float trim_left, float trim_right, float gain,
+                   const double* lut, double srate, int clip, float attack, float decay) {
+  if (n == 0 || C < 2) return n;
+  if (autogain) {                                               /* calculateAutoGain(bufferLL, bufferRR) */
+    double energy = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+      double l = (double)ch[0][i], r = (double)ch[1][i];
+      energy += l * l + r * r;
+    }
+    float ag = 1.0f;
+    if (energy > 0.0) {
+      double a = 1.0 / sqrt(energy);
+      if (a > 1.0) a = 1.0;
+      ag = (float)a;
+    }
+    for (int c = 0; c < C; ++c) for (size_t i = 0; i < n; ++i) ch[c][i] *= ag;
+  }
+  if (reverse)
+    for (int c = 0; c < C; ++c)
+      for (size_t i = 0; i < n / 2; ++i) { float t = ch[c][i]; ch[c][i] = ch[c][n - 1 - i]; ch[c][n - 1 - i] = t; }
+  {                                                             /* applyTrim */
+    size_t start = (size_t)(trim_left * (float)n);
+    size_t end = n - (size_t)(trim_right * (float)n);
+    if (start >= end || start >= n || end > n) return 0;
+    if (start > 0) for (int c = 0; c < C; ++c) memmove(ch[c], ch[c] + start, (end - start) * sizeof(float));
+    n = end - start;
+  }
+  for (int c = 0; c < C; ++c) for (size_t i = 0; i < n; ++i) ch[c][i] *= gain;       /* applyGain */
+  if (lut) for (int c = 0; c < C; ++c) oc_apply_decay(ch[c], n, lut, srate);        /* applyDecayEQ */
+  if (clip)
+    for (int c = 0; c < C; ++c)
+      for (size_t i = 0; i < n; ++i) { float v = ch[c][i]; ch[c][i] = v < -1.f ? -1.f : (v > 1.f ? 1.f : v); }
+  {                                                             /* applyEnvelope */
+    int size = (int)n;
+    int attackSize = (int)(attack * (float)size);
+    int decaySize = (int)(decay * (float)size);
+    for (int i = 0; i < attackSize; ++i) {
+      float g = (float)i / (float)attackSize;
+      for (int c = 0; c < C; ++c) ch[c][i] *= g;
+    }
+    for (int i = 0; i < decaySize; ++i) {
+      float t = (float)i / (float)decaySize;
+      float g = 1.0f - (float)pow((double)t, 0.5);
+      int idx = size - decaySize + i;
+      for (int c = 0; c < C; ++c) ch[c][idx] *= g;
+    }
+  }
+  return n;
+}

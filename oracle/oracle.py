@@ -332,6 +332,23 @@ def apply_decay(ir, lut, srate: float) -> np.ndarray:
     return buf
 
 
+def ir_shape(irs, autogain=True, reverse=False, trim_left=0.0, trim_right=0.0, gain=1.0, lut=None, srate=48000.0,
+             clip=True, attack=0.0, decay=0.0):
+    """C restatement of the device-resident subset of Impulse::recalcImpulse (chain_oracle.c::oc_ir_shape); returns the
+    shaped channels (possibly shorter: trim)."""
+    lib = _lib("oc")
+    lib.oc_ir_shape.restype = C.c_size_t
+    lib.oc_ir_shape.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                C.c_double, C.c_int, C.c_float, C.c_float]
+    bufs = [np.array(a, dtype=np.float32, copy=True) for a in irs]
+    n = bufs[0].size
+    ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+    l = None if lut is None else np.ascontiguousarray(lut, dtype=np.float64)
+    m = lib.oc_ir_shape(ptrs, len(bufs), n, int(autogain), int(reverse), trim_left, trim_right, gain,
+                        l.ctypes.data if l is not None else None, float(srate), int(clip), attack, decay)
+    return [b[:m].copy() for b in bufs]
+
+
 def ref_apply_decay(ir, lut, srate: float) -> np.ndarray:
     """The same STFT loop driven through the reference's own compiled AudioFFT (oracle/ref_shim.cpp::ref_stft_decay)."""
     lib = _lib("ref")

@@ -31,6 +31,12 @@ class ChainConfig(C.Structure):
                 ("wetgain", C.c_float), ("true_stereo", C.c_int)]
 
 
+class IrShapeParams(C.Structure):
+    _fields_ = [("autogain", C.c_int), ("reverse", C.c_int), ("trim_left", C.c_float), ("trim_right", C.c_float),
+                ("gain", C.c_float), ("decay_lut", C.c_void_p), ("srate", C.c_double), ("clip", C.c_int),
+                ("attack", C.c_float), ("decay", C.c_float)]
+
+
 class StageInfo(C.Structure):
     _fields_ = [
         ("block", C.c_size_t),
@@ -83,6 +89,9 @@ SYMBOLS = [
     ("b200conv_unregister_host", C.c_int, [C.c_void_p]),
     ("b200conv_chain_configure", C.c_int, [C.c_void_p, C.c_void_p]),
     ("b200conv_chain_process", C.c_int, [C.c_void_p, _PP, C.c_void_p, C.c_void_p, _PP, C.c_size_t]),
+    ("b200conv_ir_shape", C.c_int, [C.c_int, _PP, C.c_int, C.c_size_t, C.c_void_p, _PP, C.c_void_p]),
+    ("b200conv_init_uniform_shaped", C.c_int, [C.c_void_p, C.c_size_t, _PP, C.c_size_t, C.c_void_p]),
+    ("b200conv_init_twostage_shaped", C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _PP, C.c_size_t, C.c_void_p]),
     ("b200conv_alloc_host", C.c_void_p, [C.c_size_t]),
     ("b200conv_free_host", None, [C.c_void_p]),
     ("b200conv_version", C.c_char_p, []),

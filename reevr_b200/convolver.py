@@ -65,6 +65,28 @@ class Engine:
         keep, ptrs, lens = self._irs(irs)
         return self._check(self._l.b200conv_init_twostage(self._h, head, tail, ptrs, lens), "init_twostage", True) == 0
 
+    @staticmethod
+    def _shape_params(autogain=True, reverse=False, trim_left=0.0, trim_right=0.0, gain=1.0, lut=None, srate=48000.0,
+                      clip=True, attack=0.0, decay=0.0):
+        keep = None if lut is None else np.ascontiguousarray(lut, dtype=np.float64)
+        sp = _lib.IrShapeParams(int(autogain), int(reverse), trim_left, trim_right, gain,
+                                keep.ctypes.data if keep is not None else None, float(srate), int(clip), attack, decay)
+        return sp, keep
+
+    def init_twostage_shaped(self, head: int, tail: int, raw_irs, **shape) -> bool:
+        """IR shaping (Impulse::recalcImpulse subset) on the device, partition spectra built from the device-resident
+        taps (b200conv_init_twostage_shaped); raw_irs: equally long raw channels."""
+        keep, ptrs, lens = self._irs(raw_irs)
+        sp, lut = self._shape_params(**shape)
+        return self._check(self._l.b200conv_init_twostage_shaped(self._h, head, tail, ptrs, keep[0].size, C.byref(sp)),
+                           "init_twostage_shaped", True) == 0
+
+    def init_uniform_shaped(self, block: int, raw_irs, **shape) -> bool:
+        keep, ptrs, lens = self._irs(raw_irs)
+        sp, lut = self._shape_params(**shape)
+        return self._check(self._l.b200conv_init_uniform_shaped(self._h, block, ptrs, keep[0].size, C.byref(sp)),
+                           "init_uniform_shaped", True) == 0
+
     def init_stages(self, blocks, offsets, irs) -> bool:
         keep, ptrs, lens = self._irs(irs)
         b = (C.c_size_t * len(blocks))(*blocks)
@@ -275,6 +297,20 @@ def ir_decay_eq(ir, lut, srate: float, device: int = 0, lib=None) -> np.ndarray:
     if rc != 0:
         raise B200ConvError(f"b200conv_ir_decay_eq failed ({rc})")
     return buf
+
+
+def ir_shape(raw_irs, device: int = 0, lib=None, **shape):
+    """Device version of the Impulse::recalcImpulse subset (b200conv_ir_shape); returns the shaped channels."""
+    lib = lib or _lib.default()
+    raws = [np.ascontiguousarray(a, dtype=np.float32) for a in raw_irs]
+    n = raws[0].size
+    outs = [np.empty(max(n, 1), np.float32) for _ in raws]
+    sp, lut = Engine._shape_params(**shape)
+    m = C.c_size_t(0)
+    rc = lib.b200conv_ir_shape(device, _ptr_array(raws), len(raws), n, C.byref(sp), _ptr_array(outs), C.byref(m))
+    if rc != 0:
+        raise B200ConvError(f"b200conv_ir_shape failed ({rc})")
+    return [o[:m.value].copy() for o in outs]
 
 
 class FFTConvolver:

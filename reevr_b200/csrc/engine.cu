@@ -152,9 +152,13 @@ struct b200conv {
   float* c_ring = nullptr;           // [2][ring] predelay ring
   size_t c_ring_size = 0;
   long long c_ring_pos = 0;
+  // b200conv_init_*_shaped: the taps handed to init are DEVICE buffers (shaped there) with known post-trim lengths
+  bool ir_on_device = false;
+  const size_t* ir_trimmed = nullptr;
   // tuning / A-B switches (b200conv_set_option; defaults from the environment)
   bool opt_rt = std::getenv("B200CONV_NO_RT") == nullptr;
   bool opt_fft512 = std::getenv("B200CONV_NO_FFT512") == nullptr;
+  bool opt_slice_tail = true;        // sliced calls: also transform the last P blocks of the call (full-state contract)
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -729,11 +733,18 @@ int build_stage(b200conv* h, Stage& s, const float* const* ir, const std::vector
       long long n = (long long)len_c[c] - first;
       n = std::max(0LL, std::min(n, (long long)taps_per_c));
       nvalid[c] = (int)n;
-      if (n > 0) std::memcpy(&host[(size_t)c * taps_per_c], ir[c] + s.tap_off + first, (size_t)n * sizeof(float));
+      if (n > 0 && !h->ir_on_device) std::memcpy(&host[(size_t)c * taps_per_c], ir[c] + s.tap_off + first, (size_t)n * sizeof(float));
     }
     float* dtaps = nullptr; int* dnv = nullptr;
     CU_CHECK(h, cudaMalloc(&dtaps, host.size() * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&dnv, C * sizeof(int)));
+    if (h->ir_on_device) {        // taps shaped on the device: no host round trip
+      CU_CHECK(h, cudaMemsetAsync(dtaps, 0, host.size() * sizeof(float), h->s_main));
+      for (int c = 0; c < C; ++c)
+        if (nvalid[c] > 0)
+          CU_CHECK(h, cudaMemcpyAsync(dtaps + (size_t)c * taps_per_c, ir[c] + s.tap_off + (size_t)s.p_begin * B,
+                                      (size_t)nvalid[c] * sizeof(float), cudaMemcpyDeviceToDevice, h->s_main));
+    } else
     CU_CHECK(h, cudaMemcpyAsync(dtaps, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
     CU_CHECK(h, cudaMemcpyAsync(dnv, nvalid.data(), C * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
     pc::FwdParams fp{};
@@ -813,7 +824,8 @@ int init_impl(b200conv* h, int n_stages, const size_t* blocks, const size_t* off
   std::vector<size_t> L(C);
   size_t Lir = 0;
   for (int c = 0; c < C; ++c) {
-    L[c] = (ir && ir[c] && ir_len) ? trimmed_len(ir[c], ir_len[c]) : 0;
+    if (h->ir_on_device) L[c] = (ir && ir[c] && h->ir_trimmed) ? std::min(h->ir_trimmed[c], ir_len[c]) : 0;
+    else L[c] = (ir && ir[c] && ir_len) ? trimmed_len(ir[c], ir_len[c]) : 0;
     Lir = std::max(Lir, L[c]);
   }
   h->ir_len = L;
@@ -1198,27 +1210,19 @@ int run_group(b200conv* h, const float* in_dev, size_t in_stride, float* out_dev
 
       // Y[yb] rows >= 1 may still be read by the post work of two groups ago
       if (overlap) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb], 0));
-      if (si == 0 && h->yprev_stale) {
-        // overlap state after a forward-FFT-only advance (time-slice sharding): Y row 0 := sum_p H[p] X[head-1-p],
-        // the spectrum of the block in front of this group, from the timeline (one-block streaming sweep)
+      // overlap state after a forward-FFT-only advance (time-slice sharding): Y row 0 must become
+      // sum_p H[p] X[head-1-p], the spectrum of the block in front of this group — its input spectra are in the
+      // timeline, so the sweep simply starts one block early and writes that block as row 0
+      const int extra = (si == 0 && h->yprev_stale) ? 1 : 0;
+      if (extra) {
         if (overlap) CU_CHECK(h, cudaStreamWaitEvent(h->s_main, s.ev_post[yb ^ 1], 0));   // row 0 was written on s_post
-        pc::CmacParams c0{};
-        c0.H = s.H; c0.h_cstride = (long long)s.Prows * B;
-        c0.X = s.X; c0.x_cstride = (long long)s.R * B; c0.xrow0 = s.head - 1 - s.p_begin;
-        c0.Y = Yb; c0.y_cstride = B; c0.y_rstride = (long long)row; c0.yrow0 = 0;
-        c0.B = B; c0.Ppad = s.P; c0.nblocks = 1;
-        const bool tm = h->timing; h->timing = false;       // not a launch of the dominant (batched) sweep
-        const int variant = h->cfg.cmac_variant; h->cfg.cmac_variant = 0;
-        const int rc0 = launch_cmac(h, c0, C);
-        h->timing = tm; h->cfg.cmac_variant = variant;
-        if (rc0) return rc0;
         h->yprev_stale = false;
       }
       pc::CmacParams cp{};
       cp.H = s.H; cp.h_cstride = (long long)s.Prows * B;
-      cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin;
-      cp.Y = Yb; cp.y_cstride = B; cp.y_rstride = (long long)row; cp.yrow0 = 1;
-      cp.B = B; cp.Ppad = s.P; cp.nblocks = nb;
+      cp.X = s.X; cp.x_cstride = (long long)s.R * B; cp.xrow0 = s.head - s.p_begin - extra;
+      cp.Y = Yb; cp.y_cstride = B; cp.y_rstride = (long long)row; cp.yrow0 = 1 - extra;
+      cp.B = B; cp.Ppad = s.P; cp.nblocks = nb + extra;
       if (int rc = launch_cmac(h, cp, C)) return rc;
       if (overlap) {
         CU_CHECK(h, cudaEventRecord(s.ev_sweep[yb], h->s_main));
@@ -1329,6 +1333,10 @@ int plan_slice(b200conv* h, size_t len, int rank, int count, SlicePlan* sp) {
   // block t needs X[t-p], p < P, and the overlap-add needs the spectrum of block t-1 as well: P blocks of history
   sp->lo = sp->b > sp->a ? std::max(0LL, sp->a - P) : sp->a;
   sp->tail_lo = std::max(sp->b, T - P);
+  // Without the tail the handle's history ends with its own slice: enough for a following sliced call whose slice
+  // starts at least P blocks into the call (it uploads its own history then) — what every rank but 0 of a steady
+  // batch job needs; saves P blocks of H2D + forward FFT per call.
+  if (!h->opt_slice_tail && sp->b > sp->a) sp->tail_lo = T;
   if (sp->b <= sp->a) { sp->a = sp->b = sp->lo = std::max(0LL, T - P); sp->tail_lo = sp->a; }   // empty slice: only keep the tail
   return 0;
 }
@@ -1660,6 +1668,44 @@ int b200conv_init_stages(b200conv_t* h, int n_stages, const size_t* blocks, cons
   if (n_stages < 1 || n_stages > 4 || !blocks || !offsets || offsets[0] != 0)
     return fail(h, B200CONV_EINVAL, "need 1..4 stages with offsets[0] == 0");
   return init_common(h, n_stages, blocks, offsets, ir, ir_len);
+}
+
+// irshape.cu (internal): shape raw host taps into device buffers
+int pc_ir_shape_to_device(int device, const float* const* raw, int C, size_t n, const b200conv_ir_shape_params* sp,
+                          float** dev_out, size_t* out_len, size_t* trimmed);
+void pc_ir_shape_free(float** dev_out, int C);
+
+static int init_shaped(b200conv_t* h, int n_stages, const size_t* blocks, const size_t* offsets,
+                       const float* const* raw, size_t n, const b200conv_ir_shape_params* sp) {
+  if (!raw || !sp) return fail(h, B200CONV_EINVAL, "null argument");
+  if (h->C < 2 || h->C > 8) return fail(h, B200CONV_ESTATE, "IR shaping works on 2..8 channel handles (LL, RR[, LR, RL])");
+  float* dev[8] = {};
+  size_t m = 0, trimmed[8] = {}, lens[8] = {};
+  if (int rc = pc_ir_shape_to_device(h->cfg.device, raw, h->C, n, sp, dev, &m, trimmed))
+    return fail(h, rc, "IR shaping on the device failed");
+  for (int c = 0; c < h->C; ++c) lens[c] = m;
+  h->ir_on_device = true; h->ir_trimmed = trimmed;
+  const int rc = init_common(h, n_stages, blocks, offsets, dev, lens);
+  h->ir_on_device = false; h->ir_trimmed = nullptr;
+  pc_ir_shape_free(dev, h->C);
+  return rc;
+}
+
+int b200conv_init_uniform_shaped(b200conv_t* h, size_t block, const float* const* raw, size_t n, const b200conv_ir_shape_params* sp) {
+  REQUIRE_CUDA(h);
+  const size_t off = 0;
+  return init_shaped(h, 1, &block, &off, raw, n, sp);
+}
+
+int b200conv_init_twostage_shaped(b200conv_t* h, size_t head_block, size_t tail_block, const float* const* raw, size_t n,
+                                  const b200conv_ir_shape_params* sp) {
+  REQUIRE_CUDA(h);
+  if (head_block == 0 || tail_block == 0) return fail(h, B200CONV_EINVAL, "block size 0");
+  if (head_block > tail_block) std::swap(head_block, tail_block);
+  const size_t hb = next_pow2(head_block), tb = next_pow2(tail_block);
+  const size_t blocks[2] = {hb, tb};
+  const size_t offsets[2] = {0, 2 * tb};
+  return init_shaped(h, 2, blocks, offsets, raw, n, sp);
 }
 
 int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride,
@@ -2208,6 +2254,7 @@ int b200conv_set_option(b200conv_t* h, const char* name, int value) {
   const std::string n(name);
   if (n == "rt") h->opt_rt = value != 0;
   else if (n == "fft512") h->opt_fft512 = value != 0;
+  else if (n == "slice_keep_tail") h->opt_slice_tail = value != 0;
   else return fail(h, B200CONV_EINVAL, "unknown option");
   return B200CONV_OK;
 }

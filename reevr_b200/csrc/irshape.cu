@@ -16,7 +16,9 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -164,15 +166,13 @@ void emu_stft(const float* x, long long n, const float* win, const float2* tw, c
 
 }  // namespace
 
-extern "C" int b200conv_ir_decay_eq(int device, float* ir, size_t n, const double* lut, double srate) {
-  if (!ir || !lut) return B200CONV_EINVAL;
-  if (n == 0) return B200CONV_OK;
-  // window (Impulse.cpp:65-69) and twiddles on the host, in the layout of kernels.cuh
-  std::vector<float> win(kN);
+// window (Impulse.cpp:65-69) and twiddles on the host, in the layout of kernels.cuh
+static void stft_tables(std::vector<float>& win, std::vector<float2>& tw) {
+  win.resize(kN);
   const float step = 2.0f * 3.14159265358979323846f / (float)kN;
   for (int i = 0; i < kN / 2; ++i) win[i] = 0.42f - 0.50f * std::cos((float)i * step) + 0.08f * std::cos(2.0f * (float)i * step);
   for (int i = kN / 2; i < kN; ++i) win[i] = win[kN - 1 - i];
-  std::vector<float2> tw(pc::tw_table_len(kM));
+  tw.resize(pc::tw_table_len(kM));
   for (int k = 0; k <= kM / 2; ++k) {
     const double a = -2.0 * M_PI * (double)k / (2.0 * (double)kM);
     tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
@@ -187,49 +187,257 @@ extern "C" int b200conv_ir_decay_eq(int device, float* ir, size_t n, const doubl
       }
     p *= R;
   }
+}
+
+// The decay-EQ STFT on DEVICE-resident taps, in place, C channels of n taps at dx + c * stride: one set of tables and
+// scratch buffers for all channels, everything on stream st (no host synchronisation inside).
+struct DecayScratch {
+  float* dwin = nullptr; float* dscratch = nullptr; float* dtmp = nullptr;
+  float2* dtw = nullptr; float2* dspec = nullptr; float2* dzero = nullptr; double* dlut = nullptr;
+  void release() {
+    cudaFree(dwin); cudaFree(dscratch); cudaFree(dtmp); cudaFree(dtw); cudaFree(dspec); cudaFree(dzero); cudaFree(dlut);
+    *this = DecayScratch();
+  }
+};
+
+static bool decay_eq_device(float* dx, size_t stride, int C, size_t n, const double* lut, double srate, cudaStream_t st,
+                            DecayScratch& sc, std::vector<float>& win, std::vector<float2>& tw) {
+  if (n == 0) return true;
+  stft_tables(win, tw);
   const int skip = (int)std::ceil(100.0 * srate / (1000.0 * (double)kN));       // EARLY_REFLECTIONS_MS = 100, :612
   const long long nblocks = ((long long)n + kHop - 1) / kHop;
 #if defined(PC_EMULATE)
-  (void)device;
+  (void)st; (void)sc;
   std::vector<float> out(n);
-  emu_stft(ir, (long long)n, win.data(), tw.data(), lut, skip, out.data());
-  std::memcpy(ir, out.data(), n * sizeof(float));
+  for (int c = 0; c < C; ++c) {
+    emu_stft(dx + (size_t)c * stride, (long long)n, win.data(), tw.data(), lut, skip, out.data());
+    std::memcpy(dx + (size_t)c * stride, out.data(), n * sizeof(float));
+  }
+  return true;
+#else
+  bool ok = cudaMalloc(&sc.dtmp, n * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dwin, kN * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dtw, tw.size() * sizeof(float2)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dlut, (kM + 1) * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dspec, (size_t)nblocks * kM * sizeof(float2)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dzero, kM * sizeof(float2)) == cudaSuccess;
+  ok = ok && cudaMalloc(&sc.dscratch, (size_t)nblocks * kN * sizeof(float)) == cudaSuccess;
+  if (!ok) return false;
+  const size_t smem = 2 * kM * sizeof(float2);
+  cudaFuncSetAttribute(k_stft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_stft_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemcpyAsync(sc.dwin, win.data(), kN * sizeof(float), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(sc.dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(sc.dlut, lut, (kM + 1) * sizeof(double), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(sc.dzero, 0, kM * sizeof(float2), st);
+  const int NT = pc::fft_threads(kM);
+  for (int c = 0; c < C; ++c) {
+    float* x = dx + (size_t)c * stride;
+    k_stft_fwd<<<(unsigned)nblocks, NT, smem, st>>>(x, (long long)n, sc.dwin, sc.dtw, sc.dspec, nblocks);
+    k_stft_decay<<<dim3((kM + 255) / 256, (unsigned)nblocks), 256, 0, st>>>(sc.dspec, sc.dlut, nblocks, skip);
+    k_stft_inv<<<(unsigned)nblocks, NT, smem, st>>>(sc.dspec, sc.dzero, sc.dtw, sc.dscratch, nblocks);
+    k_stft_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc.dscratch, sc.dwin, sc.dtmp, (long long)n, nblocks);
+    cudaMemcpyAsync(x, sc.dtmp, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
+  return cudaGetLastError() == cudaSuccess;
+#endif
+}
+
+extern "C" int b200conv_ir_decay_eq(int device, float* ir, size_t n, const double* lut, double srate) {
+  if (!ir || !lut) return B200CONV_EINVAL;
+  if (n == 0) return B200CONV_OK;
+  std::vector<float> win; std::vector<float2> tw;
+#if defined(PC_EMULATE)
+  (void)device;
+  DecayScratch sc;
+  decay_eq_device(ir, n, 1, n, lut, srate, nullptr, sc, win, tw);
   return B200CONV_OK;
 #else
   if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200CONV_ECUDA; }
-  float *dx = nullptr, *dwin = nullptr, *dscratch = nullptr, *dout = nullptr;
-  float2 *dtw = nullptr, *dspec = nullptr, *dzero = nullptr;
-  double* dlut = nullptr;
+  float* dx = nullptr;
   cudaStream_t st = nullptr;
+  DecayScratch sc;
   bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMalloc(&dx, n * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dout, n * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dwin, kN * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dtw, tw.size() * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dlut, (kM + 1) * sizeof(double)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dspec, (size_t)nblocks * kM * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dzero, kM * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&dscratch, (size_t)nblocks * kN * sizeof(float)) == cudaSuccess;
   if (ok) {
-    const size_t smem = 2 * kM * sizeof(float2);
-    cudaFuncSetAttribute(k_stft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_stft_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemcpyAsync(dx, ir, n * sizeof(float), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dwin, win.data(), kN * sizeof(float), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dlut, lut, (kM + 1) * sizeof(double), cudaMemcpyHostToDevice, st);
-    cudaMemsetAsync(dzero, 0, kM * sizeof(float2), st);
-    const int NT = pc::fft_threads(kM);
-    k_stft_fwd<<<(unsigned)nblocks, NT, smem, st>>>(dx, (long long)n, dwin, dtw, dspec, nblocks);
-    k_stft_decay<<<dim3((kM + 255) / 256, (unsigned)nblocks), 256, 0, st>>>(dspec, dlut, nblocks, skip);
-    k_stft_inv<<<(unsigned)nblocks, NT, smem, st>>>(dspec, dzero, dtw, dscratch, nblocks);
-    k_stft_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dscratch, dwin, dout, (long long)n, nblocks);
-    cudaMemcpyAsync(ir, dout, n * sizeof(float), cudaMemcpyDeviceToHost, st);
-    ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    ok = decay_eq_device(dx, n, 1, n, lut, srate, st, sc, win, tw);
+    cudaMemcpyAsync(ir, dx, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
   }
-  cudaFree(dx); cudaFree(dout); cudaFree(dwin); cudaFree(dtw); cudaFree(dlut); cudaFree(dspec); cudaFree(dzero); cudaFree(dscratch);
+  sc.release();
+  cudaFree(dx);
   if (st) cudaStreamDestroy(st);
   if (!ok) { cudaGetLastError(); return B200CONV_ECUDA; }
   return B200CONV_OK;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The device-resident subset of Impulse::recalcImpulse (src/dsp/Impulse.cpp:297-360), in the reference's order:
+// auto gain (:313-320, calculateAutoGain :703-720) -> reverse (:322-330) -> trim (:437-470) -> gain (:472-486) ->
+// decay EQ (:602-648) -> clip (:488-501) -> attack / decay envelope (:651-680).  Resampling, stretch and the
+// parametric EQ (JUCE interpolators / SVF class) stay on the host.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+// dst[i] = (raw[src index of i] * autogain) * gain, src index = trim start + i, mirrored when reversed
+PC_HD float ir_pick(const float* raw, long long n_raw, long long start, int reverse, float ag, float g, long long i) {
+  const long long j = start + i;
+  const float v = raw[reverse ? n_raw - 1 - j : j];
+  return (v * ag) * g;
+}
+PC_HD float ir_clip_env(float v, int clip, long long i, long long n, long long attack_n, long long decay_n) {
+  if (clip) v = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+  if (i < attack_n) v *= (float)i / (float)attack_n;
+  if (i >= n - decay_n) {
+    const float t = (float)(i - (n - decay_n)) / (float)decay_n;
+    v *= 1.0f - (float)std::pow((double)t, 0.5);
+  }
+  return v;
+}
+
+#if !defined(PC_EMULATE)
+__global__ void k_ir_energy(const float* l, const float* r, long long n, double* out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = (double)l[i], b = (double)r[i];
+    acc += a * a + b * b;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+__global__ void k_ir_pick(float* dst, const float* raw, long long n_raw, long long start, long long n, int reverse, float ag, float g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = ir_pick(raw, n_raw, start, reverse, ag, g, i);
+}
+__global__ void k_ir_clip_env(float* x, long long n, int clip, long long attack_n, long long decay_n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = ir_clip_env(x[i], clip, i, n, attack_n, decay_n);
+}
+// 1 + index of the last tap with |h| >= 1e-6 (the trim rule of FFTConvolver.cpp:103-106), 0 if none
+__global__ void k_ir_last_significant(const float* x, long long n, unsigned long long* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(fabsf(x[i]) < 0.000001f)) atomicMax(out, (unsigned long long)(i + 1));
+}
+#endif
+}  // namespace
+
+// internal (not part of the C ABI): shapes C raw channels (host) into C device buffers dev_out[c] (cudaMalloc'ed here,
+// *out_len taps each, caller frees) and reports the post-trim lengths trimmed[c] that FFTConvolver::init would use
+extern "C" int pc_ir_shape_to_device(int device, const float* const* raw, int C, size_t n, const b200conv_ir_shape_params* sp,
+                                     float** dev_out, size_t* out_len, size_t* trimmed) {
+  if (!raw || !sp || !dev_out || !out_len || C < 2 || C > 8) return B200CONV_EINVAL;
+  for (int c = 0; c < C; ++c) dev_out[c] = nullptr;
+  // applyTrim (:437-445)
+  const size_t start = (size_t)(sp->trim_left * (float)n);
+  const size_t end = n - (size_t)(sp->trim_right * (float)n);
+  if (n == 0 || start >= end || start >= n || end > n) { *out_len = 0; for (int c = 0; c < C; ++c) if (trimmed) trimmed[c] = 0; return B200CONV_OK; }
+  const size_t m = end - start;
+  *out_len = m;
+  const long long attack_n = (long long)(int)(sp->attack * (float)(int)m), decay_n = (long long)(int)(sp->decay * (float)(int)m);
+#if defined(PC_EMULATE)
+  (void)device;
+  double energy = 0.0;
+  for (size_t i = 0; i < n; ++i) { const double a = raw[0][i], b = raw[1][i]; energy += a * a + b * b; }
+  float ag = 1.0f;
+  if (sp->autogain && energy > 0.0) ag = (float)std::min(1.0 / std::sqrt(energy), 1.0);
+  std::vector<float> win; std::vector<float2> tw;
+  DecayScratch sc;
+  for (int c = 0; c < C; ++c) {
+    dev_out[c] = (float*)std::malloc(m * sizeof(float));
+    for (size_t i = 0; i < m; ++i) dev_out[c][i] = ir_pick(raw[c], (long long)n, (long long)start, sp->reverse, ag, sp->gain, (long long)i);
+    if (sp->decay_lut) decay_eq_device(dev_out[c], m, 1, m, sp->decay_lut, sp->srate, nullptr, sc, win, tw);
+    for (size_t i = 0; i < m; ++i) dev_out[c][i] = ir_clip_env(dev_out[c][i], sp->clip, (long long)i, (long long)m, attack_n, decay_n);
+    if (trimmed) { size_t t = m; while (t > 0 && std::fabs(dev_out[c][t - 1]) < 0.000001f) --t; trimmed[c] = t; }
+  }
+  return B200CONV_OK;
+#else
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200CONV_ECUDA; }
+  cudaStream_t st = nullptr;
+  float* draw = nullptr; double* denergy = nullptr; unsigned long long* dlast = nullptr;
+  DecayScratch sc;
+  std::vector<float> win; std::vector<float2> tw;
+  bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&draw, (size_t)C * n * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc(&denergy, sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&dlast, C * sizeof(unsigned long long)) == cudaSuccess;
+  for (int c = 0; c < C && ok; ++c) ok = cudaMalloc(&dev_out[c], m * sizeof(float)) == cudaSuccess;
+  float ag = 1.0f;
+  if (ok) {
+    for (int c = 0; c < C; ++c) cudaMemcpyAsync(draw + (size_t)c * n, raw[c], n * sizeof(float), cudaMemcpyHostToDevice, st);   // the ONE upload
+    if (sp->autogain) {
+      double energy = 0.0;
+      cudaMemsetAsync(denergy, 0, sizeof(double), st);
+      k_ir_energy<<<296, 256, 0, st>>>(draw, draw + n, (long long)n, denergy);
+      cudaMemcpyAsync(&energy, denergy, sizeof(double), cudaMemcpyDeviceToHost, st);
+      ok = cudaStreamSynchronize(st) == cudaSuccess;
+      if (ok && energy > 0.0) ag = (float)std::min(1.0 / std::sqrt(energy), 1.0);
+    }
+  }
+  if (ok) {
+    const unsigned gb = (unsigned)((m + 255) / 256);
+    for (int c = 0; c < C; ++c)
+      k_ir_pick<<<gb, 256, 0, st>>>(dev_out[c], draw + (size_t)c * n, (long long)n, (long long)start, (long long)m, sp->reverse, ag, sp->gain);
+    if (sp->decay_lut)
+      for (int c = 0; c < C && ok; ++c) {
+        DecayScratch one;
+        ok = decay_eq_device(dev_out[c], m, 1, m, sp->decay_lut, sp->srate, st, one, win, tw);
+        cudaStreamSynchronize(st);
+        one.release();
+      }
+    cudaMemsetAsync(dlast, 0, C * sizeof(unsigned long long), st);
+    for (int c = 0; c < C; ++c) {
+      k_ir_clip_env<<<gb, 256, 0, st>>>(dev_out[c], (long long)m, sp->clip, attack_n, decay_n);
+      k_ir_last_significant<<<gb, 256, 0, st>>>(dev_out[c], (long long)m, dlast + c);
+    }
+    unsigned long long last[8] = {};
+    cudaMemcpyAsync(last, dlast, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    ok = ok && cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    if (trimmed) for (int c = 0; c < C; ++c) trimmed[c] = (size_t)last[c];
+  }
+  sc.release();
+  cudaFree(draw); cudaFree(denergy); cudaFree(dlast);
+  if (st) cudaStreamDestroy(st);
+  if (!ok) {
+    for (int c = 0; c < C; ++c) { cudaFree(dev_out[c]); dev_out[c] = nullptr; }
+    cudaGetLastError();
+    return B200CONV_ECUDA;
+  }
+  return B200CONV_OK;
+#endif
+}
+
+extern "C" void pc_ir_shape_free(float** dev_out, int C) {
+  for (int c = 0; c < C; ++c) {
+#if defined(PC_EMULATE)
+    std::free(dev_out[c]);
+#else
+    cudaFree(dev_out[c]);
+#endif
+    dev_out[c] = nullptr;
+  }
+}
+
+// stand-alone: the shaped taps back on the host (tests, waveform display)
+extern "C" int b200conv_ir_shape(int device, const float* const* raw, int n_channels, size_t n, const b200conv_ir_shape_params* sp,
+                                 float* const* out, size_t* out_len) {
+  if (!out || !out_len) return B200CONV_EINVAL;
+  float* dev[8] = {};
+  size_t m = 0;
+  const int rc = pc_ir_shape_to_device(device, raw, n_channels, n, sp, dev, &m, nullptr);
+  if (rc != B200CONV_OK) return rc;
+  *out_len = m;
+  bool ok = true;
+  for (int c = 0; c < n_channels && m > 0; ++c) {
+#if defined(PC_EMULATE)
+    std::memcpy(out[c], dev[c], m * sizeof(float));
+#else
+    ok = ok && cudaMemcpy(out[c], dev[c], m * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+#endif
+  }
+  pc_ir_shape_free(dev, n_channels);
+  return ok ? B200CONV_OK : B200CONV_ECUDA;
 }

@@ -74,6 +74,29 @@ def test_sliced_and_plain_calls_mix(lib, G):
     assert peak_err(y, o.process(x)) <= TOL
 
 
+def test_sliced_without_tail_on_the_later_ranks(lib):
+    """steady batch job: ranks whose slice starts >= P blocks into the call skip the tail (slice_keep_tail = 0)"""
+    B, P, G = 64, 9, 4
+    irs = [orc.synth_ir(P * B - 3)]
+    T = 60
+    xs = [orc.synth_input(3 * T * B)]
+    engs = [Engine(1, lib=lib) for _ in range(G)]
+    for g, e in enumerate(engs):
+        assert e.init_uniform(B, irs)
+        if g > 0:
+            e.set_option("slice_keep_tail", 0)
+    out = np.zeros_like(xs[0])
+    for call in range(3):
+        seg = [np.ascontiguousarray(xs[0][call * T * B:(call + 1) * T * B])]
+        o = [np.full(T * B, np.nan, np.float32)]
+        for g in range(G):
+            engs[g].process_sliced(seg, o, g, G)
+        out[call * T * B:(call + 1) * T * B] = o[0]
+    ref = orc.OracleUniform()
+    ref.init(B, irs[0])
+    assert peak_err(out, ref.process(xs[0])) <= TOL
+
+
 def test_sliced_device_resident_matches_host_path(lib):
     import ctypes as C
     if b"EMULATED" in lib.b200conv_version():

@@ -110,6 +110,8 @@ struct b200conv {
   cudaEvent_t ev_rt = nullptr;       // real-time kernel of the current call done (s_main)
   float* hpin_in_dev = nullptr;      // device-side addresses of the pinned staging buffers (zero-copy I/O)
   float* hpin_out_dev = nullptr;
+  unsigned long long* stream_ticket = nullptr;   // ticket counters of the dynamic streaming sweep (device, 256 words)
+  unsigned long long stream_ticket_base = 0;
   unsigned int* hflag = nullptr;     // pinned completion word of the real-time kernel (+ its device-side address)
   unsigned int* hflag_dev = nullptr;
   unsigned int flag_epoch = 0;
@@ -355,6 +357,8 @@ bool stream_set_smem_attr() {
   ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * pc::kStreamStageBytes + 64) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * pc::kStreamStageBytes + 128) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * pc::kStreamStageBytes + 256) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma_dyn<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * pc::kStreamStageBytes + 256) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(pc::k_cmac_stream_tma_dyn<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * pc::kStreamStageBytes + 512) == cudaSuccess;
   return ok;
 }
 #define PC_FOR_EACH_LOG2(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
@@ -554,6 +558,17 @@ int launch_cmac_stream_rows(b200conv* h, const pc::CmacParams& P, int C) {
 // TMA-fed streaming sweep (one block per launch, B >= 64): see kernels_stream.cuh.  S ring stages of 16 KB per
 // CTA, `per_sm` CTAs per SM (S * per_sm * 16 KB <= 192 KB of shared memory per SM in flight).
 template <int S>
+int launch_stream_tma_dyn_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
+#if defined(PC_EMULATE)
+  pc::emu_cmac_stream_tma_dyn({(int)grid.x, (int)grid.y, (int)grid.z}, S_);
+#else
+  const size_t smem = (size_t)S * pc::kStreamStageBytes + 16 * S + 8 * S;
+  pc::k_cmac_stream_tma_dyn<S><<<grid, dim3(288, 1, 1), smem, h->s_launch>>>(S_);
+#endif
+  return 0;
+}
+
+template <int S>
 int launch_stream_tma_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
 #if defined(PC_EMULATE)
   pc::emu_cmac_stream_tma({(int)grid.x, (int)grid.y, (int)grid.z}, S_);
@@ -564,7 +579,7 @@ int launch_stream_tma_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
   return 0;
 }
 
-int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stages, int per_sm) {
+int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stages, int per_sm, bool dynamic = false) {
   pc::StreamParams S{};
   S.H = P.H; S.h_cstride = P.h_cstride;
   S.X = P.X; S.x_cstride = P.x_cstride; S.xrow0 = P.xrow0;
@@ -576,9 +591,29 @@ int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stag
   int nsplit = std::max(1, (per_sm * h->n_sm) / std::max(1, xt * C));
   nsplit = std::max(1, std::min(nsplit, std::max(1, P.Ppad / (2 * PP))));
   S.nsplit = nsplit;
-  if (nsplit > 1 || RG > 1)
+  if (!dynamic && (nsplit > 1 || RG > 1))
     CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_launch));
   dim3 grid(xt, nsplit, C);
+  if (dynamic) {
+    if (xt * C > 256) return fail(h, B200CONV_EINVAL, "too many ticket counters");
+    if (!h->stream_ticket) {
+      CU_CHECK(h, cudaMalloc(&h->stream_ticket, 256 * sizeof(unsigned long long)));
+      CU_CHECK(h, cudaMemsetAsync(h->stream_ticket, 0, 256 * sizeof(unsigned long long), h->s_launch));
+      h->stream_ticket_base = 0;
+    }
+    nsplit = std::max(1, std::min((per_sm * h->n_sm) / std::max(1, xt * C), std::max(1, P.Ppad / (2 * PP))));
+    S.nsplit = nsplit;
+    grid = dim3(xt, nsplit, C);
+    S.ticket = h->stream_ticket; S.ticket_base = h->stream_ticket_base; S.chunk_stages = 2;
+    h->stream_ticket_base += (unsigned long long)pc::stream_dyn_chunks(S.P, PP, S.chunk_stages) + (unsigned long long)nsplit;
+    CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_launch));   // always RED.ADD
+    int idd = timing_begin(h, kKindCmac);
+    if (stages == 12) launch_stream_tma_dyn_s<12>(h, S, grid); else launch_stream_tma_dyn_s<6>(h, S, grid);
+    timing_end(h, idd);
+    h->launches++;
+    CU_CHECK(h, cudaGetLastError());
+    return 0;
+  }
   int id = timing_begin(h, kKindCmac);
   switch (stages) {
     case 2: launch_stream_tma_s<2>(h, S, grid); break;
@@ -603,6 +638,10 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;
+  }
+  if (variant == 106 || variant == 107) {      // dynamic chunk tickets: 106 = 6 stages x 2 CTAs/SM, 107 = 12 x 1
+    if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");
+    return launch_cmac_stream_tma(h, P, C, variant == 106 ? 6 : 12, variant == 106 ? 2 : 1, true);
   }
   if (variant >= 102 && variant <= 105) {
     if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");
@@ -1613,6 +1652,7 @@ void b200conv_destroy(b200conv_t* h) {
     if (h->s_tail) cudaStreamSynchronize(h->s_tail);
     free_all(h);
     if (h->ev_rt) cudaEventDestroy(h->ev_rt);
+    cudaFree(h->stream_ticket); h->stream_ticket = nullptr;
     if (h->s_tail) cudaStreamDestroy(h->s_tail);
     for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int i = 0; i < 2; ++i) {

@@ -616,6 +616,9 @@ struct StreamParams {
   const float2* X; long long x_cstride; long long xrow0;
   float2* Y; long long y_cstride, y_rstride, yrow0;   // rows must be zero before the launch when nsplit > 1
   int B, P, nblocks, nsplit;
+  // dynamic variant (k_cmac_stream_tma_dyn): one ticket counter per (channel, bin tile); counters only grow, launch k
+  // starts at ticket_base (every launch takes nchunks + nsplit tickets per counter)
+  unsigned long long* ticket; unsigned long long ticket_base; int chunk_stages;
 };
 
 #if defined(__CUDACC__)

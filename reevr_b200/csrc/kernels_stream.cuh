@@ -201,4 +201,143 @@ inline void emu_cmac_stream_tma(EmuDim grid, const StreamParams& P) {
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------
+// Dynamic variant: the partition range is cut into chunks of `chunk_stages` ring stages and the CTAs of a (channel,
+// bin tile) column draw chunk tickets from a global counter instead of owning a fixed slice.  A 35 us kernel whose
+// CTAs all stream the same number of bytes still ends ragged (DRAM channel / L2 slice contention differs per SM): with
+// tickets the fast CTAs take more chunks and the tail of the kernel shrinks to one chunk.  The producer draws the
+// next ticket while it issues the copies of the current chunk (the atomic's round trip hides behind the ring), tells the
+// consumers each stage's partition range through shared memory (written before the arrive that opens the stage) and
+// closes with an empty stage.  Every CTA draws exactly one ticket beyond the last chunk, so a launch always consumes
+// nchunks + nsplit tickets per counter and the host can advance `ticket_base` without ever resetting the counters.
+// ---------------------------------------------------------------------------------------------------------
+PC_HD int stream_dyn_chunks(int P, int PP, int KS) { return (P + PP * KS - 1) / (PP * KS); }
+
+#if defined(__CUDACC__)
+// grid (B / W, nsplit, C), block 288; dynamic smem = S*16 KB + 16*S (barriers) + 8*S (stage descriptors)
+template <int S>
+__global__ void __launch_bounds__(288) k_cmac_stream_tma_dyn(StreamParams P) {
+  extern __shared__ __align__(128) unsigned char pc_stream_smem[];
+  float2* ring = reinterpret_cast<float2*>(pc_stream_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(pc_stream_smem + (size_t)S * kStreamStageBytes);
+  unsigned long long* empty = full + S;
+  int* stage_p0 = reinterpret_cast<int*>(empty + S);      // first partition of the stage
+  int* stage_np = stage_p0 + S;                            // partitions in the stage, 0 = no more work
+  const int W = stream_tma_w(P.B), PP = stream_tma_pp(P.B), RG = stream_tma_rg(P.B);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * W, c = blockIdx.z;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  constexpr int kStageElems = kStreamStageBytes / 8;
+  if (warp == 8) {                                           // ---- producer
+    if (lane == 0) {
+      unsigned long long* ctr = P.ticket + (size_t)c * gridDim.x + blockIdx.x;
+      const int KS = P.chunk_stages, nchunks = stream_dyn_chunks(P.P, PP, KS);
+      long long t = (long long)(atomicAdd(ctr, 1ull) - P.ticket_base);
+      int i = 0;
+      while (t < nchunks) {
+        const long long tn = (long long)(atomicAdd(ctr, 1ull) - P.ticket_base);   // next ticket, in flight during this chunk
+        const int c_lo = (int)t * PP * KS;
+        const int c_hi = (c_lo + PP * KS < P.P) ? c_lo + PP * KS : P.P;
+        for (int p0 = c_lo; p0 < c_hi; p0 += PP, ++i) {
+          const int s = i % S;
+          if (i >= S) mbar_wait(&empty[s], ((i / S) - 1) & 1);
+          const int np = (c_hi - p0 < PP) ? c_hi - p0 : PP;
+          stage_p0[s] = p0; stage_np[s] = np;
+          mbar_expect_tx(&full[s], (unsigned)(np * 2 * W * 8));
+          float2* st = ring + (size_t)s * kStageElems;
+          if (W == P.B) {
+            bulk_g2s(st, stream_src_h(P, c, k0, p0), (unsigned)(np * W * 8), &full[s]);
+            bulk_g2s(st + (size_t)PP * W, stream_src_x(P, c, k0, p0 + np - 1), (unsigned)(np * W * 8), &full[s]);
+          } else {
+            for (int j = 0; j < np; ++j) {
+              bulk_g2s(st + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
+              bulk_g2s(st + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (unsigned)(W * 8), &full[s]);
+            }
+          }
+        }
+        t = tn;
+      }
+      const int s = i % S;                                   // closing stage: np = 0
+      if (i >= S) mbar_wait(&empty[s], ((i / S) - 1) & 1);
+      stage_np[s] = 0;
+      mbar_arrive(&full[s]);
+    }
+    return;
+  }
+  // ---- consumers
+  const int col = tid % (W / 2), rg = tid / (W / 2);
+  const bool packed_first = (k0 + 2 * col) == 0;
+  float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  bool any = false;
+  for (int i = 0;; ++i) {
+    const int s = i % S;
+    mbar_wait(&full[s], (i / S) & 1);
+    const int np = stage_np[s];
+    if (np == 0) break;
+    any = true;
+    stream_consume_stage(ring + (size_t)s * kStageElems, W, PP, np, col, rg, RG, packed_first, W == P.B, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (any) {
+    float* y = reinterpret_cast<float*>(P.Y + (long long)c * P.y_cstride + P.yrow0 * P.y_rstride + k0 + 2 * col);
+    atomicAdd(y + 0, acc[0].x); atomicAdd(y + 1, acc[0].y);
+    atomicAdd(y + 2, acc[1].x); atomicAdd(y + 3, acc[1].y);
+  }
+}
+#else
+// CPU emulation: tickets are drawn in CTA order (the first CTA of a column takes every chunk); same stage arithmetic
+inline void emu_cmac_stream_tma_dyn(EmuDim grid, const StreamParams& P) {
+  const int W = stream_tma_w(P.B), PP = stream_tma_pp(P.B), RG = stream_tma_rg(P.B);
+  float2* stage = new float2[kStreamStageBytes / 8];
+  const int KS = P.chunk_stages, nchunks = stream_dyn_chunks(P.P, PP, KS);
+  for (int c = 0; c < grid.z; ++c)
+    for (int bx = 0; bx < grid.x; ++bx) {
+      unsigned long long* ctr = P.ticket + (size_t)c * grid.x + bx;
+      for (int by = 0; by < grid.y; ++by) {
+        const int k0 = bx * W;
+        float2* accs = new float2[2 * 256];
+        for (int t = 0; t < 512; ++t) accs[t] = make_float2(0.f, 0.f);
+        bool any = false;
+        for (;;) {
+          const long long t = (long long)((*ctr)++ - P.ticket_base);
+          if (t >= nchunks) break;
+          const int c_lo = (int)t * PP * KS;
+          const int c_hi = (c_lo + PP * KS < P.P) ? c_lo + PP * KS : P.P;
+          for (int p0 = c_lo; p0 < c_hi; p0 += PP) {
+            const int np = (c_hi - p0 < PP) ? c_hi - p0 : PP;
+            if (W == P.B) {
+              std::memcpy(stage, stream_src_h(P, c, k0, p0), (size_t)np * W * 8);
+              std::memcpy(stage + (size_t)PP * W, stream_src_x(P, c, k0, p0 + np - 1), (size_t)np * W * 8);
+            } else {
+              for (int j = 0; j < np; ++j) {
+                std::memcpy(stage + (size_t)j * W, stream_src_h(P, c, k0, p0 + j), (size_t)W * 8);
+                std::memcpy(stage + (size_t)(PP + j) * W, stream_src_x(P, c, k0, p0 + j), (size_t)W * 8);
+              }
+            }
+            any = true;
+            for (int tid = 0; tid < 256; ++tid) {
+              const int col = tid % (W / 2), rg = tid / (W / 2);
+              stream_consume_stage(stage, W, PP, np, col, rg, RG, (k0 + 2 * col) == 0, W == P.B, accs + 2 * tid);
+            }
+          }
+        }
+        if (any)
+          for (int tid = 0; tid < 256; ++tid) {
+            const int col = tid % (W / 2);
+            float* y = reinterpret_cast<float*>(P.Y + (long long)c * P.y_cstride + P.yrow0 * P.y_rstride + k0 + 2 * col);
+            const float2* a = accs + 2 * tid;
+            y[0] += a[0].x; y[1] += a[0].y; y[2] += a[1].x; y[3] += a[1].y;
+          }
+        delete[] accs;
+      }
+    }
+  delete[] stage;
+}
+#endif
+
 }  // namespace pc

@@ -256,7 +256,7 @@ def test_cmac_variants(lib, variant):
     assert peak_err(y, o.run(x, 64)) <= TOL
 
 
-@pytest.mark.parametrize("variant", [100, 101, 102, 103, 104, 105])
+@pytest.mark.parametrize("variant", [100, 101, 102, 103, 104, 105, 106, 107])
 @pytest.mark.parametrize("B,nparts", [(64, 37), (128, 9), (512, 21), (1024, 5), (2048, 3)])
 def test_streaming_sweep_variants(lib, variant, B, nparts):
     """One block per launch (the real-time call): register-batch and TMA-ring forms of the streaming sweep, block

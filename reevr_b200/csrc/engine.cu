@@ -634,7 +634,13 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   if (variant == 0) {
     // streaming sweep for real-time calls; packed-FMA batched sweep otherwise (TT = 16 when the
     // launch group is long enough to fill 16-block tiles, TT = 8 below that)
-    if (P.nblocks == 1 && P.B >= 64 && P.Ppad >= 1) variant = 103;     // TMA ring, 6 stages x 2 CTAs/SM (best on the 120 s IR)
+    if (P.nblocks == 1 && P.B >= 64 && P.Ppad >= 1) {
+      // TMA ring: 6 stages x 2 CTAs/SM for working sets beyond L2 and multi-tile rows (0.81 of the HBM peak on the
+      // 120 s IR, 0.98 on an 8192-bin tail stage); 12 stages x 1 CTA/SM for rows below 512 bins and L2-resident
+      // single-tile shapes (fewer CTAs to ramp up) — profiles/r02_stream_variants2.txt
+      const size_t bytes = (size_t)P.Ppad * P.B * 16 * (size_t)C;
+      variant = (P.B < 512 || (P.B == 512 && bytes <= (size_t)32 << 20)) ? 104 : 103;
+    }
     else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;
@@ -1430,7 +1436,7 @@ int run_tail_block(b200conv* h, Stage& s) {
 
 constexpr size_t kRtMaxBytesPerCta = 384 * 1024;      // H + FDL bytes one CTA of the cluster may have to stream
 
-// CTAs per convolver for the cluster kernel, 0 = the call does not qualify
+// CTAs per convolver for the cluster kernel; -1 = split mode (head stage too large for one cluster); 0 = the call does not qualify
 int rt_cluster_ctas(const b200conv* h, size_t len) {
   if (!h->opt_rt || h->stages.empty() || h->stages.size() > 4) return 0;
   if (h->cfg.shard_count != 1 || h->p2p_on || h->timing || h->yprev_stale) return 0;
@@ -1446,7 +1452,8 @@ int rt_cluster_ctas(const b200conv* h, size_t len) {
   // one SM pulls ~20-50 GB/s out of L2 with this access pattern: spread a convolver over as many CTAs as the
   // cluster allows until a CTA streams <= 64 KB; beyond kRtMaxBytesPerCta the all-SM streaming sweep wins
   while (nc < max_nc && bytes / nc > 64 * 1024) nc *= 2;
-  if (nc > max_nc || bytes / nc > kRtMaxBytesPerCta) return 0;
+  if (nc > max_nc || bytes / nc > kRtMaxBytesPerCta)
+    return (C <= 8 && M >= 64) ? -1 : 0;        // -1: split mode (front kernel, all-SM TMA sweep, back kernel)
   return nc;
 }
 
@@ -1510,25 +1517,50 @@ int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, 
   P.out = out; P.out_stride = (long long)out_stride;
   P.mix_on = h->route_on ? 1 : 0; P.n_out = h->route_on ? h->n_out : C;
   std::memcpy(P.mix, h->mix, sizeof(P.mix));
-  if (use_flag && h->hflag_dev) { P.done_flag = h->hflag_dev; P.done_val = ++h->flag_epoch; }
+  const bool split = nc < 0;
+  if (split) nc = 1;
+  P.NC = nc;
+  auto launch = [&](const pc::RtParams& Q) -> int {
 #if defined(PC_EMULATE)
-  pc::emu_rt_block(P);
+    pc::emu_rt_block(Q);
 #else
-  const size_t smem = (size_t)pc::rt_smem_layout(M, C).bytes;
-  cudaError_t e = cudaErrorInvalidValue;
-  switch (M) {
-    case 16: e = rt_launch_m<16>(P, C * nc, smem, h->s_main); break;
-    case 32: e = rt_launch_m<32>(P, C * nc, smem, h->s_main); break;
-    case 64: e = rt_launch_m<64>(P, C * nc, smem, h->s_main); break;
-    case 128: e = rt_launch_m<128>(P, C * nc, smem, h->s_main); break;
-    case 256: e = rt_launch_m<256>(P, C * nc, smem, h->s_main); break;
-    case 512: e = rt_launch_m<512>(P, C * nc, smem, h->s_main); break;
-    case 1024: e = rt_launch_m<1024>(P, C * nc, smem, h->s_main); break;
-    default: break;
-  }
-  CU_CHECK(h, e);
+    const size_t smem = (size_t)pc::rt_smem_layout(M, C).bytes;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (M) {
+      case 16: e = rt_launch_m<16>(Q, C * nc, smem, h->s_main); break;
+      case 32: e = rt_launch_m<32>(Q, C * nc, smem, h->s_main); break;
+      case 64: e = rt_launch_m<64>(Q, C * nc, smem, h->s_main); break;
+      case 128: e = rt_launch_m<128>(Q, C * nc, smem, h->s_main); break;
+      case 256: e = rt_launch_m<256>(Q, C * nc, smem, h->s_main); break;
+      case 512: e = rt_launch_m<512>(Q, C * nc, smem, h->s_main); break;
+      case 1024: e = rt_launch_m<1024>(Q, C * nc, smem, h->s_main); break;
+      default: break;
+    }
+    CU_CHECK(h, e);
 #endif
-  h->launches++;
+    h->launches++;
+    return 0;
+  };
+  if (!split) {
+    if (use_flag && h->hflag_dev) { P.done_flag = h->hflag_dev; P.done_val = ++h->flag_epoch; }
+    if (int rc = launch(P)) return rc;
+  } else {
+    // head stage too large for one cluster: FRONT (assemble + forward FFT + timeline row), the TMA streaming sweep
+    // over all SMs into Y row 1, BACK (overlap-add + inverse FFT + output) — still zero-copy I/O and no D2H/H2D
+    float2* Yb = s0.Y[s0.ybuf];
+    const size_t row = (size_t)C * M;
+    P.mode = 1;
+    if (int rc = launch(P)) return rc;
+    pc::CmacParams cp{};
+    cp.H = s0.H; cp.h_cstride = (long long)s0.Prows * M;
+    cp.X = s0.X; cp.x_cstride = (long long)s0.R * M; cp.xrow0 = s0.head - s0.p_begin;
+    cp.Y = Yb; cp.y_cstride = M; cp.y_rstride = (long long)row; cp.yrow0 = 1;
+    cp.B = M; cp.Ppad = s0.P; cp.nblocks = 1;
+    if (int rc = launch_cmac(h, cp, C)) return rc;
+    P.mode = 2; P.Yt = Yb + row;
+    if (use_flag && h->hflag_dev) { P.done_flag = h->hflag_dev; P.done_val = ++h->flag_epoch; }
+    if (int rc = launch(P)) return rc;
+  }
   // bookkeeping of the head stage
   if (P.complete) { s0.head += 1; s0.blocks_done += 1; s0.fill = 0; s0.ybuf ^= 1; }
   else s0.fill += (int)len;

@@ -49,6 +49,10 @@ struct RtParams {
   // completion word in pinned host memory (nullptr: none): set to done_val once every output sample is written, so
   // that the caller can spin on it instead of paying the driver's stream-synchronise latency
   unsigned int* done_flag; unsigned int done_val;
+  // mode 0: the whole step in this launch.  Head stages too large for one cluster (uniform long IRs) split it:
+  // mode 1 = FRONT (phases A, B: assemble, forward FFT, timeline row) -> the all-SM TMA sweep (K2t) writes Yt ->
+  // mode 2 = BACK (phase E from the global row Yt: overlap-add, inverse FFT, output, overlap row of the next block)
+  int mode; const float2* Yt;
 };
 
 // shared-memory layout of one CTA (float2 units unless noted)
@@ -221,60 +225,73 @@ __global__ void __launch_bounds__(256) k_rt_block(RtParams P) {
 
   // ---- A: twiddles + the open block
   for (int j = tid; j < tw_table_len(M); j += 256) tw[j] = P.tw[j];
-  for (int i = tid; i < M; i += 256) rt_assemble(P, c, q, i, xs);
-  __syncthreads();
-
-  // ---- B: forward real FFT -> xnew
-  if constexpr (M == 1) {
-    if (tid == 0) { bufA[0] = make_float2(xs[0], 0.0f); }
+  if (P.mode != 2) {
+    for (int i = tid; i < M; i += 256) rt_assemble(P, c, q, i, xs);
     __syncthreads();
-    if (tid == 0) fwd_split(bufA, xnew, tw, M, 0);
-  } else {
-    constexpr int R0 = pass_radix(M, 1);
-    for (int i = tid; i < M / R0; i += 256)
-      stockham_butterfly<false>(RtSmemIn{xs, P.fill + P.len}, SmemOut{bufA}, tw + tw_pass_offset(M, 1), M, 1, R0, i);
+
+    // ---- B: forward real FFT -> xnew
+    if constexpr (M == 1) {
+      if (tid == 0) { bufA[0] = make_float2(xs[0], 0.0f); }
+      __syncthreads();
+      if (tid == 0) fwd_split(bufA, xnew, tw, M, 0);
+    } else {
+      constexpr int R0 = pass_radix(M, 1);
+      for (int i = tid; i < M / R0; i += 256)
+        stockham_butterfly<false>(RtSmemIn{xs, P.fill + P.len}, SmemOut{bufA}, tw + tw_pass_offset(M, 1), M, 1, R0, i);
+      __syncthreads();
+      float2* res = rt_fwd_passes<M, R0>(bufA, bufB, tw, tid);
+      for (int k = tid; k <= M / 2; k += 256) fwd_split(res, xnew, tw, M, k);
+    }
     __syncthreads();
-    float2* res = rt_fwd_passes<M, R0>(bufA, bufB, tw, tid);
-    for (int k = tid; k <= M / 2; k += 256) fwd_split(res, xnew, tw, M, k);
-  }
-  __syncthreads();
-  if (q == 0) {
-    float2* row = P.X + (long long)c * P.x_cstride + P.head * (long long)M;
-    for (int k = tid; k < M; k += 256) row[k] = xnew[k];
+    if (q == 0) {
+      float2* row = P.X + (long long)c * P.x_cstride + P.head * (long long)M;
+      for (int k = tid; k < M; k += 256) row[k] = xnew[k];
+    }
+    if (P.mode == 1) return;            // FRONT: the sweep is a separate all-SM launch (uniform across the cluster)
   }
 
-  // ---- C: sweep of this CTA's bin tile
-  const int pairs = rt_pairs(M, P.NC);
-  const int PG = 256 / pairs;                 // host guarantees 1 <= pairs <= 256
-  const int pi = tid % pairs, pg = tid / pairs;
-  const int k = q * (M / P.NC) + 2 * pi;
-  if (pg < PG) {
-    const float4c r = rt_sweep_thread(P, c, k, pg, PG, xnew);
-    red[tid] = make_float4(r.a.x, r.a.y, r.b.x, r.b.y);
-  }
-  __syncthreads();
-  // ---- D: reduce the partition groups, tile -> q = 0 CTA of the convolver (DSMEM), overlap row of the next block
-  if (tid < pairs) {
-    float4 v = red[tid];
-    for (int g = 1; g < PG; ++g) {
-      const float4 u = red[tid + g * pairs];
-      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  const float2* Yt_src = yfull;
+  if (P.mode == 0) {
+    // ---- C: sweep of this CTA's bin tile
+    const int pairs = rt_pairs(M, P.NC);
+    const int PG = 256 / pairs;                 // host guarantees 1 <= pairs <= 256
+    const int pi = tid % pairs, pg = tid / pairs;
+    const int k = q * (M / P.NC) + 2 * pi;
+    if (pg < PG) {
+      const float4c r = rt_sweep_thread(P, c, k, pg, PG, xnew);
+      red[tid] = make_float4(r.a.x, r.a.y, r.b.x, r.b.y);
     }
-    float2* dst = rt_map_rank(yfull, (unsigned)(c * P.NC));
-    dst[k] = make_float2(v.x, v.y);
-    dst[k + 1] = make_float2(v.z, v.w);
-    if (P.complete) {
-      float2* yn = P.Ynext + (long long)c * P.y_cstride + k;
-      yn[0] = make_float2(v.x, v.y);
-      yn[1] = make_float2(v.z, v.w);
+    __syncthreads();
+    // ---- D: reduce the partition groups, tile -> q = 0 CTA of the convolver (DSMEM), overlap row of the next block
+    if (tid < pairs) {
+      float4 v = red[tid];
+      for (int g = 1; g < PG; ++g) {
+        const float4 u = red[tid + g * pairs];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      float2* dst = rt_map_rank(yfull, (unsigned)(c * P.NC));
+      dst[k] = make_float2(v.x, v.y);
+      dst[k + 1] = make_float2(v.z, v.w);
+      if (P.complete) {
+        float2* yn = P.Ynext + (long long)c * P.y_cstride + k;
+        yn[0] = make_float2(v.x, v.y);
+        yn[1] = make_float2(v.z, v.w);
+      }
     }
+    rt_cluster_sync();
+  } else {                                      // BACK: the sweep's row is in global memory
+    Yt_src = P.Yt + (long long)c * P.y_cstride;
+    if (P.complete && q == 0) {
+      float2* yn = P.Ynext + (long long)c * P.y_cstride;
+      for (int k = tid; k < M; k += 256) yn[k] = Yt_src[k];
+    }
+    __syncthreads();                            // twiddles staged
   }
-  rt_cluster_sync();
 
   // ---- E: overlap-add in the frequency domain, inverse FFT, output
   if (q == 0) {
     const float2* Yp = P.Yprev + (long long)c * P.y_cstride;
-    for (int kk = tid; kk <= M / 2; kk += 256) inv_pre(yfull, Yp, bufA, tw, M, kk, 1, 0);
+    for (int kk = tid; kk <= M / 2; kk += 256) inv_pre(Yt_src, Yp, bufA, tw, M, kk, 1, 0);
     __syncthreads();
     const float scale = 1.0f / (float)M;
     if constexpr (M == 1) {
@@ -327,7 +344,7 @@ inline void emu_rt_block(const RtParams& P) {
     ct[r].bufA = new float2[MB]; ct[r].bufB = new float2[MB]; ct[r].xnew = new float2[MB]; ct[r].yfull = new float2[MB];
     ct[r].xs = new float[M]; ct[r].ys = new float[M]; ct[r].mix = new float[(size_t)P.C * M]; ct[r].red = new float4[256];
   }
-  for (int r = 0; r < n; ++r) {
+  for (int r = 0; r < n && P.mode != 2; ++r) {
     const int c = r / P.NC, q = r % P.NC;
     Cta& t = ct[r];
     for (int i = 0; i < M; ++i) rt_assemble(P, c, q, i, t.xs);
@@ -354,7 +371,7 @@ inline void emu_rt_block(const RtParams& P) {
     }
   }
   // C + D  (q = 0 wrote the timeline row before any CTA reads older rows: rows < head only)
-  for (int r = 0; r < n; ++r) {
+  for (int r = 0; r < n && P.mode == 0; ++r) {
     const int c = r / P.NC, q = r % P.NC;
     Cta& t = ct[r];
     const int pairs = rt_pairs(M, P.NC), PG = 256 / pairs;
@@ -378,10 +395,15 @@ inline void emu_rt_block(const RtParams& P) {
     }
   }
   // E
-  for (int c = 0; c < P.C; ++c) {
+  for (int c = 0; c < P.C && P.mode != 1; ++c) {
     Cta& t = ct[c * P.NC];
     const float2* Yp = P.Yprev + (long long)c * P.y_cstride;
-    for (int kk = 0; kk <= M / 2; ++kk) inv_pre(t.yfull, Yp, t.bufA, P.tw, M, kk, 1, 0);
+    const float2* Yt_src = t.yfull;
+    if (P.mode == 2) {
+      Yt_src = P.Yt + (long long)c * P.y_cstride;
+      if (P.complete) for (int k = 0; k < M; ++k) P.Ynext[(long long)c * P.y_cstride + k] = Yt_src[k];
+    }
+    for (int kk = 0; kk <= M / 2; ++kk) inv_pre(Yt_src, Yp, t.bufA, P.tw, M, kk, 1, 0);
     const float scale = 1.0f / (float)M;
     if (M == 1) {
       t.ys[0] = t.bufA[0].x * scale;
@@ -404,7 +426,7 @@ inline void emu_rt_block(const RtParams& P) {
       if (P.mix_on) ct[0].mix[(size_t)c * M + i] = v; else P.out[(long long)c * P.out_stride + i] = v;
     }
   }
-  if (P.mix_on)
+  if (P.mix_on && P.mode != 1)
     for (int o = 0; o < P.n_out; ++o)
       for (int i = 0; i < P.len; ++i) {
         float acc = 0.0f;
@@ -414,7 +436,7 @@ inline void emu_rt_block(const RtParams& P) {
         }
         P.out[(long long)o * P.out_stride + i] = acc;
       }
-  if (P.done_flag) *P.done_flag = P.done_val;
+  if (P.done_flag && P.mode != 1) *P.done_flag = P.done_val;
   for (int r = 0; r < n; ++r) {
     delete[] ct[r].bufA; delete[] ct[r].bufB; delete[] ct[r].xnew; delete[] ct[r].yfull;
     delete[] ct[r].xs; delete[] ct[r].ys; delete[] ct[r].mix; delete[] ct[r].red;

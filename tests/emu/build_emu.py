@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "reevr_b200", "csrc")
 LIB = os.path.join(HERE, "libb200conv_emu.so")
 DEPS = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "irshape.cu"), os.path.join(CSRC, "kernels.cuh"),
+        os.path.join(CSRC, "kernels_stream.cuh"), os.path.join(CSRC, "kernels_fft512.cuh"), os.path.join(CSRC, "kernels_rt.cuh"),
+        os.path.join(CSRC, "kernels_chain.cuh"),
         os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "b200conv.h")]
 
 

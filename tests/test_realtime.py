@@ -67,6 +67,30 @@ def test_uniform_long_ir_uses_a_multi_cta_cluster(lib):
         assert peak_err(ys[c], o.process(xs[c])) <= TOL
 
 
+def test_uniform_very_long_ir_uses_the_split_mode(lib):
+    """head stage beyond one cluster's reach (1100 partitions of 256 = 4.5 MB per convolver): front kernel, all-SM TMA
+    sweep, back kernel — same zero-copy I/O, incl. a ragged pair of calls and the device mixdown"""
+    irs = [orc.synth_ir(256 * 1100 - 9, c) for c in range(2)]
+    xs = [orc.synth_input(256 * 30, c) for c in range(2)]
+    e = Engine(2, lib=lib)
+    assert e.init_uniform(256, irs)
+    l0 = e.launch_count
+    ys = stream(e, xs, [256] * 12 + [100, 156] + [256] * 17)
+    assert e.launch_count - l0 <= 31 * 3 + 2           # front + sweep + back per call, nothing else
+    for c in range(2):
+        o = orc.OracleUniform()
+        o.init(256, irs[c])
+        assert peak_err(ys[c], o.process(xs[c])) <= TOL
+    e.set_routing([0, 1], [[1, 1], [1, -1]])
+    m = stream(e, xs, [256] * 4)
+    e2 = Engine(2, lib=lib)
+    e2.set_option("rt", 0)
+    assert e2.init_uniform(256, irs)
+    stream(e2, xs, [256 * 30])
+    r = stream(e2, xs, [256] * 4)
+    assert peak_err(m[0], r[0] + r[1]) <= TOL and peak_err(m[1], r[0] - r[1]) <= TOL
+
+
 def test_quad_with_device_mixdown(lib):
     sc = StereoConvolver(lib=lib)
     sc.prepare(128)

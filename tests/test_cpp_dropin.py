@@ -44,3 +44,17 @@ def test_example_offline_render_on_gpu(tmp_path):
     from reevr_b200 import _lib
     _build_and_run(os.path.dirname(_lib.LIB_PATH), os.path.basename(_lib.LIB_PATH), str(tmp_path / "render_gpu"),
                    src=os.path.join(ROOT, "examples", "offline_render.cpp"), expect="rendered")
+
+
+def test_example_plugin_callback_on_emulation(tmp_path):
+    from tests.emu.build_emu import build
+    lib = build()
+    _build_and_run(os.path.dirname(lib), os.path.basename(lib), str(tmp_path / "callback_emu"),
+                   src=os.path.join(ROOT, "examples", "plugin_callback.cpp"), expect="rendered")
+
+
+@pytest.mark.gpu
+def test_example_plugin_callback_on_gpu(tmp_path):
+    from reevr_b200 import _lib
+    _build_and_run(os.path.dirname(_lib.LIB_PATH), os.path.basename(_lib.LIB_PATH), str(tmp_path / "callback_gpu"),
+                   src=os.path.join(ROOT, "examples", "plugin_callback.cpp"), expect="rendered")

@@ -439,8 +439,8 @@ def main():
                     fd = os.open(f"/proc/{obj[0][0]}/fd/{obj[0][1]}", os.O_RDWR)
                 mm = mmap.mmap(fd, nbytes)
                 arr = np.frombuffer(mm, dtype=np.float32).reshape(shape)
-                if rank == 0:
-                    arr[...] = 0                 # first touch on rank 0's node
+                # (no first touch here: every rank touches its OWN time slice below, while it is bound to its GPU's
+                #  CPUs, so that the pages each GPU DMAs from / into live on that GPU's NUMA node)
                 if os.environ.get("B200CONV_BENCH_NO_SHARED"):
                     ok = 0
                 elif lib.b200conv_register_host(arr.ctypes.data, nbytes) != 0:
@@ -687,7 +687,11 @@ def main():
             t = torch.empty((C, n), dtype=torch.float32).pin_memory()
             keep_alive.append(t)
             y_host = t.numpy()
-        if rank == 0 or not shared:
+        if shared:
+            for c in range(C):
+                x_host[c][a * block:b * block] = synth_input(n, c)[a * block:b * block]     # NUMA-local first touch
+                y_host[c][a * block:b * block] = 0.0
+        else:
             for c in range(C):
                 x_host[c] = synth_input(n, c)
         barrier()
@@ -861,8 +865,20 @@ def main():
             realtime["reevr_quad"] = {"call": "StereoConvolver quad, two-stage 128/8192, 10 s IRs, len 128, device mixdown (one call, 2 in / 2 out)",
                                       "median_us": med2, "p99_us": p992, "budget_us": 128 / 48000 * 1e6}
             sc._e.close()
+            # ... and the whole reverb section of processBlock on the device: dry block + send / reverb envelopes in,
+            # filters + predelay + 4 convolvers + mixdown + width + dry/wet, final mix out (b200conv_chain_process)
+            ec = Engine(4, device=local)
+            assert ec.init_twostage(128, 8192, [synth_ir(480000, c) for c in range(4)])
+            ec.chain_configure(srate=48000.0, lowcut_hz=120.0, lowcut_slope=1, highcut_hz=8000.0, highcut_slope=2, predelay=480,
+                               width=0.8, drygain=0.7, wetgain=0.7, true_stereo=True)
+            ys_, yr_ = np.full(128, 0.9, np.float32), np.full(128, 0.8, np.float32)
+            med3, p993 = latency(lambda: ec.chain_process(l_, r_, ys_, yr_), reps=600, warm_calls=200)
+            realtime["reevr_quad_chain"] = {"call": "b200conv_chain_process: send envelope + 12/24 dB cuts + predelay + quad two-stage 128/8192 "
+                                                    "+ mixdown + reverb envelope + width + dry/wet, len 128",
+                                            "median_us": med3, "p99_us": p993, "budget_us": 128 / 48000 * 1e6}
+            ec.close()
         except Exception as ex:
-            realtime = {"error": f"{type(ex).__name__}: {ex}"}
+            realtime = dict(realtime or {}, error=f"{type(ex).__name__}: {ex}")
 
     if args.sweep and rank == 0 and world == 1:
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--blocks", str(T)], stdout=sys.stderr)

@@ -151,6 +151,8 @@ struct b200conv {
   float* c_conv_in = nullptr;        // [2][Lmax] convolver input (after filters + predelay)
   float* c_filt = nullptr;           // [2][Lmax]
   float* c_state = nullptr;          // [2][8] filter states
+  float* c_hpin = nullptr;           // pinned [dry L, dry R, ysend, yrev, out L, out R][hpin_cap]: zero-copy I/O of real-time chain calls
+  float* c_hpin_dev = nullptr;
   float* c_ring = nullptr;           // [2][ring] predelay ring
   size_t c_ring_size = 0;
   long long c_ring_pos = 0;
@@ -257,6 +259,8 @@ void free_all(b200conv* h) {
   }
   cudaFree(h->dch[0]); h->dch[0] = nullptr;
   cudaFree(h->c_io); cudaFree(h->c_conv_in); cudaFree(h->c_filt); cudaFree(h->c_state); cudaFree(h->c_ring);
+  if (h->c_hpin) cudaFreeHost(h->c_hpin);
+  h->c_hpin = h->c_hpin_dev = nullptr;
   h->c_io = h->c_conv_in = h->c_filt = h->c_state = h->c_ring = nullptr;
   h->c_ring_size = 0; h->c_ring_pos = 0;
   h->chain_on = false; h->route_in_only = false;
@@ -2202,6 +2206,12 @@ int b200conv_chain_configure(b200conv_t* h, const b200conv_chain_config* cfg) {
     CU_CHECK(h, cudaMalloc(&h->c_conv_in, 2 * L * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&h->c_filt, 2 * L * sizeof(float)));
     CU_CHECK(h, cudaMalloc(&h->c_state, 2 * pc::kChainStates * sizeof(float)));
+    CU_CHECK(h, cudaMallocHost((void**)&h->c_hpin, 6 * h->hpin_cap * sizeof(float)));
+#if defined(PC_EMULATE)
+    h->c_hpin_dev = h->c_hpin;
+#else
+    if (cudaHostGetDevicePointer((void**)&h->c_hpin_dev, h->c_hpin, 0) != cudaSuccess) { cudaGetLastError(); h->c_hpin_dev = nullptr; }
+#endif
   }
   if (ring != h->c_ring_size) {
     cudaFree(h->c_ring); h->c_ring = nullptr;
@@ -2229,14 +2239,29 @@ int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* 
   const size_t L = h->Lmax, B0 = h->stages[0].B;
   const size_t chunk = L - B0;
   float* d_dry = h->c_io; float* d_send = h->c_io + 2 * L; float* d_rev = h->c_io + 3 * L; float* d_out = h->c_io + 4 * L;
+  // real-time calls: the kernels read the dry block + envelopes straight from pinned host memory and write the mix
+  // back into it (zero-copy), so a callback is three launches and one synchronise instead of six copies more
+  const bool zc = len <= h->hpin_cap && len <= chunk && h->c_hpin_dev != nullptr && h->opt_rt;
+  size_t dstride = L;
+  if (zc) {
+    const size_t cap = h->hpin_cap;
+    std::memcpy(h->c_hpin, dry[0], len * sizeof(float));
+    std::memcpy(h->c_hpin + cap, dry[1], len * sizeof(float));
+    if (ysend) std::memcpy(h->c_hpin + 2 * cap, ysend, len * sizeof(float));
+    if (yrev) std::memcpy(h->c_hpin + 3 * cap, yrev, len * sizeof(float));
+    d_dry = h->c_hpin_dev; d_send = h->c_hpin_dev + 2 * cap; d_rev = h->c_hpin_dev + 3 * cap; d_out = h->c_hpin_dev + 4 * cap;
+    dstride = cap;
+  }
   for (size_t done = 0; done < len;) {
     const size_t n = std::min(len - done, chunk);
-    for (int ch = 0; ch < 2; ++ch)
-      CU_CHECK(h, cudaMemcpyAsync(d_dry + ch * L, dry[ch] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
-    if (ysend) CU_CHECK(h, cudaMemcpyAsync(d_send, ysend + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
-    if (yrev) CU_CHECK(h, cudaMemcpyAsync(d_rev, yrev + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    if (!zc) {
+      for (int ch = 0; ch < 2; ++ch)
+        CU_CHECK(h, cudaMemcpyAsync(d_dry + ch * L, dry[ch] + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+      if (ysend) CU_CHECK(h, cudaMemcpyAsync(d_send, ysend + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+      if (yrev) CU_CHECK(h, cudaMemcpyAsync(d_rev, yrev + done, n * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    }
     pc::ChainSendParams sp{};
-    sp.dry = d_dry; sp.dry_stride = (long long)L; sp.ysend = ysend ? d_send : nullptr;
+    sp.dry = d_dry; sp.dry_stride = (long long)dstride; sp.ysend = ysend ? d_send : nullptr;
     sp.conv_in = h->c_conv_in; sp.conv_stride = (long long)L;
     sp.filt = h->c_filt; sp.filt_stride = (long long)L;
     sp.state = h->c_state;
@@ -2260,10 +2285,10 @@ int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* 
     h->route_in_only = false;
     if (rc) return rc;
     pc::ChainWetParams wp{};
-    wp.dry = d_dry; wp.dry_stride = (long long)L;
+    wp.dry = d_dry; wp.dry_stride = (long long)dstride;
     wp.conv = h->dch[0]; wp.conv_stride = (long long)L;
     wp.yrev = yrev ? d_rev : nullptr;
-    wp.out = d_out; wp.out_stride = (long long)L; wp.n = (long long)n;
+    wp.out = d_out; wp.out_stride = (long long)dstride; wp.n = (long long)n;
     wp.quad_ts = (C == 4 && h->chain_cfg.true_stereo) ? 1 : 0;
     wp.width = h->chain_cfg.width; wp.drygain = h->chain_cfg.drygain; wp.wetgain = h->chain_cfg.wetgain;
 #if defined(PC_EMULATE)
@@ -2273,9 +2298,12 @@ int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* 
     CU_CHECK(h, cudaGetLastError());
 #endif
     h->launches++;
-    for (int ch = 0; ch < 2; ++ch)
-      CU_CHECK(h, cudaMemcpyAsync(out[ch] + done, d_out + ch * L, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    if (!zc)
+      for (int ch = 0; ch < 2; ++ch)
+        CU_CHECK(h, cudaMemcpyAsync(out[ch] + done, d_out + ch * L, n * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     CU_CHECK(h, cudaStreamSynchronize(h->s_main));
+    if (zc)
+      for (int ch = 0; ch < 2; ++ch) std::memcpy(out[ch], h->c_hpin + (4 + ch) * h->hpin_cap, n * sizeof(float));
     done += n;
   }
   return B200CONV_OK;

@@ -215,21 +215,23 @@ static bool decay_eq_device(float* dx, size_t stride, int C, size_t n, const dou
   }
   return true;
 #else
-  bool ok = cudaMalloc(&sc.dtmp, n * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dwin, kN * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dtw, tw.size() * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dlut, (kM + 1) * sizeof(double)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dspec, (size_t)nblocks * kM * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dzero, kM * sizeof(float2)) == cudaSuccess;
-  ok = ok && cudaMalloc(&sc.dscratch, (size_t)nblocks * kN * sizeof(float)) == cudaSuccess;
-  if (!ok) return false;
   const size_t smem = 2 * kM * sizeof(float2);
-  cudaFuncSetAttribute(k_stft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k_stft_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaMemcpyAsync(sc.dwin, win.data(), kN * sizeof(float), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(sc.dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(sc.dlut, lut, (kM + 1) * sizeof(double), cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(sc.dzero, 0, kM * sizeof(float2), st);
+  if (!sc.dtmp) {        // scratch and tables once per shaping job, shared by all channels (same n)
+    bool ok = cudaMalloc(&sc.dtmp, n * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dwin, kN * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dtw, tw.size() * sizeof(float2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dlut, (kM + 1) * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dspec, (size_t)nblocks * kM * sizeof(float2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dzero, kM * sizeof(float2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&sc.dscratch, (size_t)nblocks * kN * sizeof(float)) == cudaSuccess;
+    if (!ok) return false;
+    cudaFuncSetAttribute(k_stft_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stft_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemcpyAsync(sc.dwin, win.data(), kN * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(sc.dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(sc.dlut, lut, (kM + 1) * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(sc.dzero, 0, kM * sizeof(float2), st);
+  }
   const int NT = pc::fft_threads(kM);
   for (int c = 0; c < C; ++c) {
     float* x = dx + (size_t)c * stride;
@@ -382,12 +384,8 @@ extern "C" int pc_ir_shape_to_device(int device, const float* const* raw, int C,
     for (int c = 0; c < C; ++c)
       k_ir_pick<<<gb, 256, 0, st>>>(dev_out[c], draw + (size_t)c * n, (long long)n, (long long)start, (long long)m, sp->reverse, ag, sp->gain);
     if (sp->decay_lut)
-      for (int c = 0; c < C && ok; ++c) {
-        DecayScratch one;
-        ok = decay_eq_device(dev_out[c], m, 1, m, sp->decay_lut, sp->srate, st, one, win, tw);
-        cudaStreamSynchronize(st);
-        one.release();
-      }
+      for (int c = 0; c < C && ok; ++c)
+        ok = decay_eq_device(dev_out[c], m, 1, m, sp->decay_lut, sp->srate, st, sc, win, tw);   // one scratch set for all channels
     cudaMemsetAsync(dlast, 0, C * sizeof(unsigned long long), st);
     for (int c = 0; c < C; ++c) {
       k_ir_clip_env<<<gb, 256, 0, st>>>(dev_out[c], (long long)m, sp->clip, attack_n, decay_n);

@@ -7,7 +7,7 @@ Metric: M stereo frames / s ("Msamples/sec stereo conv @ IR=10s/48kHz block=512"
 independent mono convolutions (LL, RR — src/dsp/StereoConvolver.cpp:35-36) with their own
 480 000-tap IR each, uniform partitions of 512 (P = 938).  One "step" = one pass of the hot
 path (forward FFT of every block, FDL complex-MAC sweep, inverse FFT + overlap-add) over a batch
-of T = 28 152 blocks (14.4 M frames = 5 min of audio) of synthetic white noise; the job is the same
+of T = 112 608 blocks (57.7 M frames = 20 min of audio) of synthetic white noise; the job is the same
 at every N ("strong" scaling).
 
 * value            device-resident throughput (input/output already in HBM), CUDA events on the
@@ -67,10 +67,11 @@ WORKLOADS = {
     "cfg2": dict(C=2, ir_s=5, sr=48000, block=128, tail=8192, desc="stereo 48 kHz, 5 s IR, two-stage head 128 / tail 8192 (config 2)"),
     "cfg3": dict(C=2, ir_s=30, sr=96000, block=64, tail=8192, desc="stereo 96 kHz, 30 s IR, two-stage head 64 / tail 8192 (config 3)"),
 }
-# 28152 blocks: the sweep grid (16 bin tiles x ceil(blocks/64) x 2 channels, 444 CTAs resident) is 31.7 / 15.9 /
-# 7.9 / 3.96 waves for 1 / 2 / 4 / 8 time slices (a slice sweeps one block more than it outputs: the overlap state of
-# its first block) — no nearly-empty last wave at any N
-T_METRIC = 28152
+# 112608 blocks (57.7 M frames = 20 min of stereo audio per step): the sweep grid (16 bin tiles x ceil(blocks/64) x
+# 2 channels, 444 CTAs resident) is 126.8 / 63.4 / 31.7 / 15.9 waves for 1 / 2 / 4 / 8 time slices (a slice sweeps one
+# block more than it outputs: the overlap state of its first block) — no nearly-empty last wave at any N, and the
+# per-call fixed costs of a slice (history upload + transforms, pipeline fill of the PCIe path) stay small at N = 8
+T_METRIC = 112608
 T_IR120 = 7104
 
 

@@ -169,6 +169,11 @@ PC_HD float rt_out_sample(const RtParams& P, int c, const float* ys, int s) {
 PC_D void rt_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// A CTA may only be written through DSMEM once it is known to have STARTED (its shared memory exists): every CTA
+// arrives on the cluster barrier first thing and waits on it right before its first remote store (split barrier, so
+// the wait is free by then).
+PC_D void rt_cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+PC_D void rt_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // generic address of `p` (own shared memory) in CTA `rank` of the cluster
 template <class T>
 PC_D T* rt_map_rank(T* p, unsigned rank) {
@@ -222,6 +227,8 @@ __global__ void __launch_bounds__(256) k_rt_block(RtParams P) {
   float* mixbuf = reinterpret_cast<float*>(pc_rt_smem + L.mixbuf);
   const int tid = threadIdx.x;
   const int rank = blockIdx.x, c = rank / P.NC, q = rank % P.NC;
+  const bool remote_stores = (P.mode == 0) || (P.mode == 2 && P.mix_on);     // uniform over the cluster
+  if (remote_stores) rt_cluster_arrive();
 
   // ---- A: twiddles + the open block
   for (int j = tid; j < tw_table_len(M); j += 256) tw[j] = P.tw[j];
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(256) k_rt_block(RtParams P) {
     }
     __syncthreads();
     // ---- D: reduce the partition groups, tile -> q = 0 CTA of the convolver (DSMEM), overlap row of the next block
+    rt_cluster_wait();                          // every CTA of the cluster has started
     if (tid < pairs) {
       float4 v = red[tid];
       for (int g = 1; g < PG; ++g) {
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(256) k_rt_block(RtParams P) {
     } else {
       rt_inv_passes<M, 1>(bufA, bufB, tw, tid, ys, scale);
     }
+    if (P.mode == 2 && P.mix_on) rt_cluster_wait();      // BACK mode: first remote store of this launch (all CTAs have q = 0)
     if (P.mix_on) {
       float* mb = rt_map_rank(mixbuf, 0u) + (long long)c * M;
       for (int i = tid; i < P.len; i += 256) mb[i] = rt_out_sample(P, c, ys, P.fill + i);

@@ -2268,7 +2268,10 @@ int b200conv_chain_process(b200conv_t* h, const float* const* dry, const float* 
     sp.ring = h->c_ring; sp.ring_stride = (long long)h->c_ring_size; sp.ring_mask = (long long)h->c_ring_size - 1;
     sp.ring_pos = h->c_ring_pos; sp.predelay = h->chain_cfg.predelay; sp.n = (long long)n;
     sp.lc = h->chain_lc; sp.hc = h->chain_hc;
-    const int T = n <= 4096 ? 64 : 1024;
+    // chunks: two passes of n/T sequential samples (~200 cycles each) + a serial scan of T 8x8 matrix-vector steps
+    // (~256 cycles each): T ~ sqrt(1.5 n), a power of two in [8, 1024]
+    int T = 8;
+    while (T < 1024 && (size_t)T * T < n + n / 2) T *= 2;
 #if defined(PC_EMULATE)
     pc::emu_chain_send(sp, T);
 #else

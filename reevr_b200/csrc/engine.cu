@@ -1446,7 +1446,7 @@ int rt_cluster_ctas(const b200conv* h, size_t len) {
   if (h->cfg.shard_count != 1 || h->p2p_on || h->timing || h->yprev_stale) return 0;
   const Stage& s0 = h->stages[0];
   const int M = s0.B, C = h->C;
-  if (M < 16 || M > 1024 || C > 16 || len == 0 || (size_t)s0.fill + len > (size_t)M) return 0;
+  if (M < 16 || M > 1024 || C > 8 || len == 0 || (size_t)s0.fill + len > (size_t)M) return 0;
   if (h->route_on && (h->n_out * (int)len > 8 * 1024)) return 0;
   int max_nc = 1;
   while (max_nc * 2 * C <= 16 && max_nc * 2 <= M / 32) max_nc *= 2;     // cluster <= 16 CTAs, tile >= 16 bin pairs
@@ -1503,7 +1503,6 @@ int rt_call(b200conv* h, int nc, const float* in, size_t in_stride, float* out, 
   P.fill = s0.fill; P.len = (int)len; P.complete = (s0.fill + (int)len == M) ? 1 : 0;
   P.in = in; P.in_stride = (long long)in_stride;
   for (int c = 0; c < 8; ++c) P.in_map[c] = (h->route_on || h->route_in_only) ? h->in_map[c] : c;
-  if (C > 8) return fail(h, B200CONV_ESTATE, "real-time kernel supports up to 8 convolvers per handle");
   P.inbuf0 = s0.inbuf; P.inbuf0_stride = (long long)s0.in_stride;
   P.H = s0.H; P.h_cstride = (long long)s0.Prows * M;
   P.X = s0.X; P.x_cstride = (long long)s0.R * M; P.head = s0.head;

@@ -128,3 +128,18 @@ def test_realtime_and_batch_calls_interleave(lib):
     o.clear()
     y2 = stream(e, [x[n:]], [64] * 40)[0]
     assert peak_err(y2, o.process(x[n:n + 64 * 40])) <= TOL
+
+
+def test_eight_convolvers_in_one_cluster(lib):
+    """config 4's channel count through the real-time path: 8 convolvers x 2 CTAs = one 16-CTA (non-portable) cluster"""
+    irs = [orc.synth_ir(128 * 40 - 3, c) for c in range(8)]
+    xs = [orc.synth_input(128 * 24, c) for c in range(8)]
+    e = Engine(8, lib=lib)
+    assert e.init_uniform(128, irs)
+    l0 = e.launch_count
+    ys = stream(e, xs, [128] * 24)
+    assert e.launch_count - l0 == 24                     # one launch per call
+    for c in range(8):
+        o = orc.OracleUniform()
+        o.init(128, irs[c])
+        assert peak_err(ys[c], o.process(xs[c])) <= TOL

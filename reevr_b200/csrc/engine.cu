@@ -583,7 +583,7 @@ int launch_stream_tma_s(b200conv* h, const pc::StreamParams& S_, dim3 grid) {
   return 0;
 }
 
-int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stages, int per_sm, bool dynamic = false) {
+int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stages, int per_sm, bool dynamic = false, float skew = -1.0f) {
   pc::StreamParams S{};
   S.H = P.H; S.h_cstride = P.h_cstride;
   S.X = P.X; S.x_cstride = P.x_cstride; S.xrow0 = P.xrow0;
@@ -598,6 +598,10 @@ int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stag
   if (!dynamic && (nsplit > 1 || RG > 1))
     CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_launch));
   dim3 grid(xt, nsplit, C);
+  if (skew >= 0.0f && !dynamic) {        // skewed static slices, channels interleaved in launch order
+    S.interleave = 1; S.skew = skew;
+    grid = dim3(xt, nsplit * C, 1);
+  }
   if (dynamic) {
     if (xt * C > 256) return fail(h, B200CONV_EINVAL, "too many ticket counters");
     if (!h->stream_ticket) {
@@ -648,6 +652,11 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
     else variant = (P.nblocks >= 64) ? 22 : 26;
+  }
+  if (variant == 108) {                        // 6 stages x 2 CTAs/SM, skewed static slices (B200CONV_STREAM_SKEW percent, default 8)
+    if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");
+    static const float skew = [] { const char* e = std::getenv("B200CONV_STREAM_SKEW"); return e ? (float)std::atof(e) / 100.0f : 0.08f; }();
+    return launch_cmac_stream_tma(h, P, C, 6, 2, false, skew);
   }
   if (variant == 106 || variant == 107) {      // dynamic chunk tickets: 106 = 6 stages x 2 CTAs/SM, 107 = 12 x 1
     if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");

@@ -619,6 +619,10 @@ struct StreamParams {
   // dynamic variant (k_cmac_stream_tma_dyn): one ticket counter per (channel, bin tile); counters only grow, launch k
   // starts at ticket_base (every launch takes nchunks + nsplit tickets per counter)
   unsigned long long* ticket; unsigned long long ticket_base; int chunk_stages;
+  // skewed static slices (k_cmac_stream_tma with interleave = 1): grid.y = nsplit * C, launch index li = blockIdx.y,
+  // channel = li % C, slice = li / C; slice sizes fall linearly with the slice index by +-skew around the mean, because
+  // CTAs are dispatched in launch order over a few microseconds and equal slices would end equally staggered
+  int interleave; float skew;
 };
 
 #if defined(__CUDACC__)

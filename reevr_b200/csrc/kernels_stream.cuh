@@ -41,6 +41,22 @@ PC_HD void stream_slice(int P, int nsplit, int y, int* p_lo, int* p_hi) {
   *p_hi = (*p_lo + per < P) ? *p_lo + per : P;
 }
 
+// skewed slices: weight of slice y = 1 + skew * (1 - 2 y / (nsplit - 1)); boundaries are multiples of `align` partitions
+PC_HD int stream_skew_bound(int P, int nsplit, int y, float skew, int align) {
+  if (y <= 0) return 0;
+  if (y >= nsplit) return P;
+  const double f = (double)y * (1.0 + (double)skew) - (nsplit > 1 ? (double)skew * (double)y * (double)(y - 1) / (double)(nsplit - 1) : 0.0);
+  long long b = (long long)((double)P * f / (double)nsplit + 0.5);
+  b = (b + align / 2) / align * align;
+  if (b < 0) b = 0;
+  if (b > P) b = P;
+  return (int)b;
+}
+PC_HD void stream_slice_skewed(int P, int nsplit, int y, float skew, int align, int* p_lo, int* p_hi) {
+  *p_lo = stream_skew_bound(P, nsplit, y, skew, align);
+  *p_hi = stream_skew_bound(P, nsplit, y + 1, skew, align);
+}
+
 // sources of the j-th partition of the stage that starts at partition p0 (W-bin segments of one row each)
 PC_HD const float2* stream_src_h(const StreamParams& P, int c, int k0, int p) {
   return P.H + (long long)c * P.h_cstride + (long long)p * P.B + k0;
@@ -102,9 +118,15 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
   unsigned long long* empty = full + S;
   const int W = stream_tma_w(P.B), PP = stream_tma_pp(P.B), RG = stream_tma_rg(P.B);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k0 = blockIdx.x * W, c = blockIdx.z;
-  int p_lo, p_hi;
-  stream_slice(P.P, P.nsplit, blockIdx.y, &p_lo, &p_hi);
+  const int k0 = blockIdx.x * W;
+  int c = blockIdx.z, p_lo, p_hi;
+  if (P.interleave) {                                        // launch order = slice-major, channels interleaved
+    const int C = gridDim.y / P.nsplit;
+    c = blockIdx.y % C;
+    stream_slice_skewed(P.P, P.nsplit, blockIdx.y / C, P.skew, PP, &p_lo, &p_hi);
+  } else {
+    stream_slice(P.P, P.nsplit, blockIdx.y, &p_lo, &p_hi);
+  }
   if (p_lo >= p_hi) return;                                  // whole CTA (uniform)
   const int nst = (p_hi - p_lo + PP - 1) / PP;
   if (tid == 0) {
@@ -161,12 +183,18 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
 inline void emu_cmac_stream_tma(EmuDim grid, const StreamParams& P) {
   const int W = stream_tma_w(P.B), PP = stream_tma_pp(P.B), RG = stream_tma_rg(P.B);
   float2* stage = new float2[kStreamStageBytes / 8];
-  for (int c = 0; c < grid.z; ++c)
+  for (int cz = 0; cz < grid.z; ++cz)
     for (int by = 0; by < grid.y; ++by)
       for (int bx = 0; bx < grid.x; ++bx) {
         const int k0 = bx * W;
-        int p_lo, p_hi;
-        stream_slice(P.P, P.nsplit, by, &p_lo, &p_hi);
+        int c = cz, p_lo, p_hi;
+        if (P.interleave) {
+          const int C = grid.y / P.nsplit;
+          c = by % C;
+          stream_slice_skewed(P.P, P.nsplit, by / C, P.skew, PP, &p_lo, &p_hi);
+        } else {
+          stream_slice(P.P, P.nsplit, by, &p_lo, &p_hi);
+        }
         if (p_lo >= p_hi) continue;
         const int nst = (p_hi - p_lo + PP - 1) / PP;
         float2* accs = new float2[2 * 256];

@@ -256,7 +256,7 @@ def test_cmac_variants(lib, variant):
     assert peak_err(y, o.run(x, 64)) <= TOL
 
 
-_STREAM_CASES = [(v, B, n) for v in (100, 101, 102, 103, 104, 105, 106, 107)
+_STREAM_CASES = [(v, B, n) for v in (100, 101, 102, 103, 104, 105, 106, 107, 108)
                  for B, n in ((64, 37), (128, 9), (512, 21), (1024, 5), (2048, 3))
                  if not (v == 100 and B > 512)]        # the generic fallback kernel is only ever selected below 64 bins
 

@@ -112,6 +112,8 @@ struct b200conv {
   float* hpin_out_dev = nullptr;
   unsigned long long* stream_ticket = nullptr;   // ticket counters of the dynamic streaming sweep (device, 256 words)
   unsigned long long stream_ticket_base = 0;
+  unsigned int stream_launches = 0;             // alternates the walk direction of the streaming sweep
+  bool opt_stream_alt = std::getenv("B200CONV_NO_STREAM_ALT") == nullptr;
   unsigned int* hflag = nullptr;     // pinned completion word of the real-time kernel (+ its device-side address)
   unsigned int* hflag_dev = nullptr;
   unsigned int flag_epoch = 0;
@@ -598,6 +600,7 @@ int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stag
   if (!dynamic && (nsplit > 1 || RG > 1))
     CU_CHECK(h, cudaMemsetAsync(S.Y + S.yrow0 * S.y_rstride, 0, (size_t)S.y_rstride * sizeof(float2), h->s_launch));
   dim3 grid(xt, nsplit, C);
+  if (!dynamic && h->opt_stream_alt) S.descending = (int)(h->stream_launches++ & 1u);
   if (skew >= 0.0f && !dynamic) {        // skewed static slices, channels interleaved in launch order
     S.interleave = 1; S.skew = skew;
     grid = dim3(xt, nsplit * C, 1);
@@ -2366,6 +2369,7 @@ int b200conv_set_option(b200conv_t* h, const char* name, int value) {
   if (n == "rt") h->opt_rt = value != 0;
   else if (n == "fft512") h->opt_fft512 = value != 0;
   else if (n == "slice_keep_tail") h->opt_slice_tail = value != 0;
+  else if (n == "stream_alternate") h->opt_stream_alt = value != 0;
   else return fail(h, B200CONV_EINVAL, "unknown option");
   return B200CONV_OK;
 }

@@ -623,6 +623,10 @@ struct StreamParams {
   // channel = li % C, slice = li / C; slice sizes fall linearly with the slice index by +-skew around the mean, because
   // CTAs are dispatched in launch order over a few microseconds and equal slices would end equally staggered
   int interleave; float skew;
+  // descending = 1: every CTA walks its slice from the last partition to the first.  The host alternates the direction
+  // from launch to launch: what the previous block step touched last is still in L2 and is what this one touches first
+  // (a working set moderately above the L2 capacity then hits for a large part instead of thrashing an LRU cache).
+  int descending;
 };
 
 #if defined(__CUDACC__)

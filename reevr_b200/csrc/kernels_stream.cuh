@@ -57,6 +57,18 @@ PC_HD void stream_slice_skewed(int P, int nsplit, int y, float skew, int align, 
   *p_hi = stream_skew_bound(P, nsplit, y + 1, skew, align);
 }
 
+// stage i of a slice [p_lo, p_hi): first partition and partition count, ascending or descending walk
+PC_HD void stream_stage_range(int p_lo, int p_hi, int PP, int i, int descending, int* p0, int* np) {
+  if (!descending) {
+    *p0 = p_lo + i * PP;
+    *np = (p_hi - *p0 < PP) ? p_hi - *p0 : PP;
+  } else {
+    const int hi = p_hi - i * PP;
+    *p0 = (hi - PP > p_lo) ? hi - PP : p_lo;
+    *np = hi - *p0;
+  }
+}
+
 // sources of the j-th partition of the stage that starts at partition p0 (W-bin segments of one row each)
 PC_HD const float2* stream_src_h(const StreamParams& P, int c, int k0, int p) {
   return P.H + (long long)c * P.h_cstride + (long long)p * P.B + k0;
@@ -140,8 +152,8 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
       for (int i = 0; i < nst; ++i) {
         const int s = i % S;
         if (i >= S) mbar_wait(&empty[s], ((i / S) - 1) & 1); // the consumers are done with this stage's previous content
-        const int p0 = p_lo + i * PP;
-        const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
+        int p0, np;
+        stream_stage_range(p_lo, p_hi, PP, i, P.descending, &p0, &np);
         mbar_expect_tx(&full[s], (unsigned)(np * 2 * W * 8));
         float2* st = ring + (size_t)s * kStageElems;
         if (W == P.B) {          // whole rows: the np rows of H (and of the FDL) are one contiguous run -> 2 copies per stage
@@ -163,8 +175,9 @@ __global__ void __launch_bounds__(288) k_cmac_stream_tma(StreamParams P) {
   float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   for (int i = 0; i < nst; ++i) {
     const int s = i % S;
-    const int p0 = p_lo + i * PP;
-    const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
+    int p0, np;
+    stream_stage_range(p_lo, p_hi, PP, i, P.descending, &p0, &np);
+    (void)p0;
     mbar_wait(&full[s], (i / S) & 1);                        // the stage's bytes have landed
     stream_consume_stage(ring + (size_t)s * kStageElems, W, PP, np, col, rg, RG, packed_first, W == P.B, acc);
     __syncwarp();
@@ -200,8 +213,8 @@ inline void emu_cmac_stream_tma(EmuDim grid, const StreamParams& P) {
         float2* accs = new float2[2 * 256];
         for (int t = 0; t < 512; ++t) accs[t] = make_float2(0.f, 0.f);
         for (int i = 0; i < nst; ++i) {
-          const int p0 = p_lo + i * PP;
-          const int np = (p_hi - p0 < PP) ? p_hi - p0 : PP;
+          int p0, np;
+          stream_stage_range(p_lo, p_hi, PP, i, P.descending, &p0, &np);
           if (W == P.B) {
             std::memcpy(stage, stream_src_h(P, c, k0, p0), (size_t)np * W * 8);
             std::memcpy(stage + (size_t)PP * W, stream_src_x(P, c, k0, p0 + np - 1), (size_t)np * W * 8);

@@ -116,7 +116,8 @@ unsigned long long b200conv_launch_count(const b200conv_t* h);
  * with zero-copy I/O, 0 = multi-kernel path), "fft512" (1 = register-resident FFT kernels for block size 512),
  * "slice_keep_tail" (default 1; 0 = b200conv_process_sliced does not upload / transform the last P blocks of the call:
  * the handle then only supports a following sliced call whose slice starts >= P blocks into the call — every rank
- * but 0 of a steady batch job — until the next b200conv_clear). */
+ * but 0 of a steady batch job — until the next b200conv_clear), "stream_alternate" (default 1: the streaming sweep
+ * walks its partition slices in alternating directions from launch to launch, see kernels_stream.cuh). */
 int    b200conv_set_option(b200conv_t* h, const char* name, int value);
 /* Device time (ms) spent in the dominant CMAC kernel / all kernels during the last
  * b200conv_process_device call, measured with CUDA events on the handle's stream

@@ -1830,6 +1830,28 @@ int b200conv_process_device(b200conv_t* h, const float* in_dev, size_t in_stride
 // Host -> device staging of one launch group (n samples per channel from in[c] + off into din[b], channel pitch
 // `pitch`) on stream st.  With the slot exchange's input broadcast only shard 0 touches PCIe: it uploads the
 // group, stores it into every peer's din[b] over NVLink and an "input landed" flag barrier releases the peers.
+// Launch-group sizes of a pipelined host-pointer call: the H2D copy of the FIRST group and the D2H copy of the LAST one
+// cannot overlap with compute, so the sequence ramps up from one sweep wave (w, 2w, 4w, ...), runs steady groups of
+// `grp` samples and ramps down again; every group but the last is a whole number of waves / 64-block tiles, the last
+// one carries whatever is left (incl. a ragged tail).
+static std::vector<size_t> ramped_groups(size_t len, size_t wave, size_t tile, size_t grp, size_t cap) {
+  std::vector<size_t> g, up;
+  size_t tot = 0;
+  for (size_t r = wave; r * 2 <= grp && 2 * (tot + r) + 2 * grp <= len; r *= 2) { up.push_back(r); tot += r; }
+  size_t remaining = len;
+  for (size_t r : up) { g.push_back(r); remaining -= r; }
+  while (remaining > tot + grp) { g.push_back(grp); remaining -= grp; }
+  if (!up.empty()) {
+    const size_t mid = (remaining - tot) / tile * tile;
+    if (mid) { g.push_back(mid); remaining -= mid; }
+    for (size_t i = up.size(); i-- > 1;) { g.push_back(up[i]); remaining -= up[i]; }
+  }
+  if (remaining) g.push_back(remaining);
+  std::vector<size_t> out;                      // no group above the staging capacity
+  for (size_t v : g) { while (v > cap) { out.push_back(cap); v -= cap; } if (v) out.push_back(v); }
+  return out;
+}
+
 static int stage_input(b200conv_t* h, int b, const float* const* in, size_t off, size_t n, size_t pitch, int Cin,
                        const float* packed_src, cudaStream_t st) {
   const bool bc = h->p2p_on && h->bcast_in;
@@ -1929,9 +1951,10 @@ static int process_impl(b200conv_t* h, const float* const* in, float* const* out
   wave = std::max(tile, wave / tile * tile);
   size_t grp = std::max(wave, (len / 8) / wave * wave);
   grp = std::min(grp, chunk >= tile ? chunk / tile * tile : chunk);
-  for (; done < len; ++i) {
+  const std::vector<size_t> groups = ramped_groups(len, wave, tile, grp, chunk);
+  for (size_t gi = 0; gi < groups.size() && done < len; ++gi, ++i) {
     const int b = i & 1;
-    const size_t n = std::min(len - done, grp);
+    const size_t n = std::min(len - done, groups[gi]);
     if (i >= 2) CU_CHECK(h, cudaStreamWaitEvent(h->s_in, h->ev_din[b], 0));     // din[b] free again
     if (int rc = stage_input(h, b, in, done, n, h->Lmax, Cin, nullptr, h->s_in)) return rc;
     CU_CHECK(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
@@ -2027,7 +2050,10 @@ int b200conv_process_sliced(b200conv_t* h, const float* const* in, float* const*
     for (size_t o = (size_t)b0 * B, e = (size_t)b1 * B; o < e; o += grp) pieces.push_back({o, std::min(grp, e - o), conv});
   };
   add(sp.lo, sp.a, false);
-  add(sp.a, sp.b, true);
+  {   // the slice itself: ramped groups (short first H2D, short last D2H)
+    size_t o = (size_t)sp.a * B;
+    for (size_t gsz : ramped_groups(n_slice, wave, tile, grp, chunk)) { pieces.push_back({o, gsz, true}); o += gsz; }
+  }
   add(sp.tail_lo, sp.T, false);
   int i = 0;
   bool used_out[2] = {false, false};

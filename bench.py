@@ -84,6 +84,17 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def measured_bf16_peaks():
+    """(burst, sustained) dense bf16 TFLOP/s of MEASURED_PEAKS.json, else the B200_PROFILING.md fallback"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))
+    return 1590.0, 1590.0
+
+
 def algorithmic_bytes_per_channel_block(P: int, block: int) -> int:
     K = block + 1
     return 16 * P * K + 8 * K + 16 * block
@@ -249,6 +260,9 @@ def cpu_reference_run(wl, seconds_target: float, threads: int, single_thread_leg
 # ---------------------------------------------------------------------------------------------
 # live DRAM-traffic capture: this script re-run under ncu in --probe mode (one kernel, one launch)
 # ---------------------------------------------------------------------------------------------
+PROBE_VARIANT = 0      # --variant of the run, handed to the traffic probe
+
+
 def ncu_traffic(which: str, kernel_regex: str, skip: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel; None (+ reason) if unavailable."""
     import shutil
@@ -259,7 +273,7 @@ def ncu_traffic(which: str, kernel_regex: str, skip: int):
            "-k", f"regex:{kernel_regex}", "-s", str(skip), "-c", "1", "--csv",
            sys.executable, os.path.abspath(__file__), "--probe", which]
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, B200CONV_BENCH_VARIANT=str(PROBE_VARIANT)))
     except Exception as ex:
         return None, f"ncu failed: {type(ex).__name__}"
     tot, seen = 0.0, 0
@@ -286,7 +300,7 @@ def probe_main(which: str):
     if which == "batch":
         wl = WORKLOADS["metric"]
         C, block, T = wl["C"], wl["block"], T_METRIC
-        eng = Engine(C, device=0, max_batch_blocks=T + 1)
+        eng = Engine(C, device=0, max_batch_blocks=T + 1, cmac_variant=int(os.environ.get("B200CONV_BENCH_VARIANT", "0")))
         assert eng.init_uniform(block, [synth_ir(wl["ir_s"] * wl["sr"], c) for c in range(C)])
         n = T * block
         x = torch.from_numpy(np.stack([synth_input(n, c) for c in range(C)])).cuda()
@@ -331,6 +345,8 @@ def main():
     args = ap.parse_args()
     if args.probe:
         return probe_main(args.probe)
+    global PROBE_VARIANT
+    PROBE_VARIANT = args.variant
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -401,6 +417,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
     hbm_peak, sm_mhz, peak_kind = measured_peaks()
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    bf16_peak, bf16_sustained = measured_bf16_peaks()
 
     def barrier():
         if world > 1:
@@ -520,6 +537,32 @@ def main():
             ffma = sum(4.0 * (int(x["p_end"]) - int(x["p_begin"])) for x in stages_all) * C * n_frames * reps / max(cm_n, 1)
         fp32_tflops = 2.0 * ffma / (per_launch_ms * 1e-3) / 1e12
         hbm_alg = alg_bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        if eng.last_sweep_variant() == 40 and len(stages_all) == 1:
+            # tensor-core sweep (kernels_tc.cuh): the timed stage is k_tc_split_x + k_tc_sweep + k_tc_merge_y.  Executed
+            # tensor flops = tiles x K chunks x 24 MMAs (3xTF32 x 2 time lines x 4 k-steps) x 2*128*128*8.
+            q = (max(Ploc - 1, 0) + 63) // 64 * 64
+            nchunk = q // 32 + 2
+            ntile = -(-(-(-int(round(blocks_per_launch)) // 64)) // 128)
+            mma_flop = float(C * block * ntile * nchunk * 24) * 2.0 * 128 * 128 * 8
+            tf32_peak = bf16_peak / 2.0
+            tflops = mma_flop / (per_launch_ms * 1e-3) / 1e12
+            return {
+                "kernel": "k_tc_sweep (tcgen05.mma kind::tf32, 3xTF32 block-Toeplitz FDL sweep) incl. k_tc_split_x / k_tc_merge_y",
+                "bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
+                "peak_source": f"half of MEASURED_PEAKS.json bf16_tflops ({peak_kind}): kind::tf32 issues at half the bf16 rate "
+                               "(tools/tc_probe.cu: 64 cycles per 128x128x8 MMA = 4096 flop/clk/SM)",
+                "frac_of_sustained_peak": tflops / (bf16_sustained / 2.0),
+                "launch_ms": per_launch_ms, "blocks_per_launch": blocks_per_launch, "partitions": Ploc,
+                "flop_per_launch": mma_flop, "traffic": None,
+                "useful_fp32_equivalent": {"achieved": fp32_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_tflops / fp32_peak,
+                                           "note": "4 FP32 FMA per complex MAC of the direct form / the same time, against the CUDA-core "
+                                                   "FMA peak the packed-FMA sweep (cmac_variant 22, frac 0.83) is bounded by"},
+                "hbm_algorithmic": {"achieved": hbm_alg, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_alg / hbm_peak,
+                                    "algorithmic_bytes_per_launch": alg_bytes_launch,
+                                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                                    "note": "SURVEY 8d streaming-form bytes / launch time; > 1 because nothing is streamed per block"},
+                "step_share": {"cmac_ms": cm_ms / reps, "fft_ms": fft_ms / reps, "ifft_ms": ifft_ms / reps},
+            }
         return {
             "kernel": "k_cmac_batch2 (batched FDL sweep, FFMA2)", "bound": "fp32",
             "achieved": fp32_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_tflops / fp32_peak,
@@ -918,7 +961,7 @@ def main():
     rc_exit = 0
     if rank == 0:
         if world == 1 and not args.no_traffic and args.workload == "metric":
-            tr, how = ncu_traffic("batch", "k_cmac_batch2", 2)
+            tr, how = ncu_traffic("batch", "k_tc_sweep" if main_res["roofline"].get("bound") == "tensor" else "k_cmac_batch2", 2)
             main_res["roofline"]["traffic"] = tr
             main_res["roofline"]["traffic_source"] = how
             if stream_roof and "error" not in stream_roof:

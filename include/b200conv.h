@@ -112,6 +112,9 @@ int    b200conv_stage(const b200conv_t* h, int s, b200conv_stage_info* out);
 size_t b200conv_ir_len(const b200conv_t* h, int channel);    /* post-trim tap count            */
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 unsigned long long b200conv_launch_count(const b200conv_t* h);
+/* Form of the FDL sweep (FFTConvolver.cpp:176-187) the last launch resolved to: 22 / 26 = packed-FMA batched sweep,
+ * 40 = tensor-core sweep (tcgen05 kind::tf32, 3xTF32), 100..108 = streaming forms.  For benchmarks and tests. */
+int b200conv_last_sweep_variant(const b200conv_t* h);
 /* Tuning / A-B switches: "rt" (1 = real-time calls that stay inside the open block run as ONE cluster-kernel launch
  * with zero-copy I/O, 0 = multi-kernel path), "fft512" (1 = register-resident FFT kernels for block size 512),
  * "slice_keep_tail" (default 1; 0 = b200conv_process_sliced does not upload / transform the last P blocks of the call:

@@ -67,6 +67,7 @@ SYMBOLS = [
     ("b200conv_stage", C.c_int, [C.c_void_p, C.c_int, C.POINTER(StageInfo)]),
     ("b200conv_ir_len", C.c_size_t, [C.c_void_p, C.c_int]),
     ("b200conv_launch_count", C.c_ulonglong, [C.c_void_p]),
+    ("b200conv_last_sweep_variant", C.c_int, [C.c_void_p]),
     ("b200conv_set_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("b200conv_last_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("b200conv_stream", C.c_void_p, [C.c_void_p]),

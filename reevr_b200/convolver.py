@@ -192,12 +192,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._l.b200conv_launch_count(self._h))
 
+    def last_sweep_variant(self) -> int:
+        """22 / 26 packed-FMA batched sweep, 40 tensor-core sweep, 100..108 streaming forms."""
+        return int(self._l.b200conv_last_sweep_variant(self._h))
+
     @property
     def stream(self) -> int:
         return int(self._l.b200conv_stream(self._h) or 0)
 
     def set_option(self, name: str, value: int):
-        """A/B switches of the engine: "rt" (one-launch real-time path), "fft512" (register-resident B = 512 FFTs)."""
+        """A/B switches of the engine: "rt" (one-launch real-time path), "fft512" (register-resident B = 512 FFTs), "tc" (tensor-core sweep for long launch groups)."""
         self._check(self._l.b200conv_set_option(self._h, name.encode(), int(value)), "set_option")
 
     def set_timing(self, on: bool):

@@ -43,6 +43,9 @@
 #include "kernels_fft512.cuh"
 #include "kernels_rt.cuh"
 #include "kernels_chain.cuh"
+#if !defined(PC_EMULATE)
+#include "kernels_tc.cuh"
+#endif
 
 namespace {
 
@@ -165,6 +168,19 @@ struct b200conv {
   bool opt_rt = std::getenv("B200CONV_NO_RT") == nullptr;
   bool opt_fft512 = std::getenv("B200CONV_NO_FFT512") == nullptr;
   bool opt_slice_tail = true;        // sliced calls: also transform the last P blocks of the call (full-state contract)
+  // tensor-core sweep (kernels_tc.cuh): Toeplitz tile images of one stage's H, per-bin time lines, partial planes
+  bool opt_tc = std::getenv("B200CONV_NO_TC") == nullptr;
+  float* tc_A = nullptr;
+  const void* tc_A_for = nullptr;    // H the images were built from (+ its geometry)
+  int tc_A_P = 0, tc_A_B = 0, tc_A_C = 0;
+  float* tc_Xt = nullptr;
+  float* tc_Yt = nullptr;
+  size_t tc_A_bytes = 0, tc_Xt_bytes = 0, tc_Yt_bytes = 0;
+  int* tc_err = nullptr;             // mapped pinned word: a barrier wait of k_tc_sweep gave up
+  int* tc_err_dev = nullptr;
+  bool tc_attr_set = false;
+  bool tc_alloc_failed = false;      // the scratch did not fit once: stay on the FFMA sweep
+  int last_variant = 0;              // sweep form the last launch_cmac resolved to (b200conv_last_sweep_variant)
   // slot exchange (fused multi-GPU path), stage 0 of a single-stage handle
   bool p2p_on = false;
   int p2p_mode = 0;
@@ -260,6 +276,10 @@ void free_all(b200conv* h) {
     h->din[i] = h->dout[i] = nullptr;
   }
   cudaFree(h->dch[0]); h->dch[0] = nullptr;
+  cudaFree(h->tc_A); cudaFree(h->tc_Xt); cudaFree(h->tc_Yt);
+  h->tc_A = h->tc_Xt = h->tc_Yt = nullptr; h->tc_A_for = nullptr; h->tc_A_bytes = h->tc_Xt_bytes = h->tc_Yt_bytes = 0;
+  if (h->tc_err) cudaFreeHost(h->tc_err);
+  h->tc_err = h->tc_err_dev = nullptr; h->tc_alloc_failed = false;
   cudaFree(h->c_io); cudaFree(h->c_conv_in); cudaFree(h->c_filt); cudaFree(h->c_state); cudaFree(h->c_ring);
   if (h->c_hpin) cudaFreeHost(h->c_hpin);
   h->c_hpin = h->c_hpin_dev = nullptr;
@@ -638,6 +658,87 @@ int launch_cmac_stream_tma(b200conv* h, const pc::CmacParams& P, int C, int stag
   return 0;
 }
 
+// ---- tensor-core sweep (kernels_tc.cuh) -------------------------------------------------------------------------
+constexpr int kTcMinBlocks = 4096;      // below that a 128-segment tile is mostly padding: the FFMA sweep is faster
+
+// can this sweep run on the tensor cores?  (geometry only; the scratch is allocated by launch_cmac_tc)
+bool tc_eligible(const b200conv* h, const pc::CmacParams& P, int C) {
+#if defined(PC_EMULATE)
+  (void)h; (void)P; (void)C;
+  return false;
+#else
+  if (P.xg > 0 || P.Ppad < 1 || P.nblocks < 1) return false;
+  const pc::tc::Geom g = pc::tc::make_geom(P.Ppad, P.nblocks);
+  if (!pc::tc::geom_ok(g, P.B)) return false;
+  return (unsigned long long)C * P.B * 4ull * (unsigned long long)g.rows < (1ull << 31);
+#endif
+}
+
+#if !defined(PC_EMULATE)
+// grow-only device scratch; a failed allocation is not an error of the call (the caller falls back to the FFMA sweep)
+bool tc_reserve(b200conv* h, float** buf, size_t* have, size_t need) {
+  if (*have >= need) return true;
+  cudaFree(*buf);
+  *buf = nullptr; *have = 0;
+  if (cudaMalloc(buf, need) != cudaSuccess) { cudaGetLastError(); *buf = nullptr; h->tc_alloc_failed = true; return false; }
+  *have = need;
+  return true;
+}
+#endif
+
+// returns 1 when the scratch could not be allocated (nothing launched), 0 on success, < 0 on error
+int launch_cmac_tc(b200conv* h, const pc::CmacParams& P, int C) {
+#if defined(PC_EMULATE)
+  (void)P; (void)C;
+  return fail(h, B200CONV_EINVAL, "the tensor-core sweep is not part of the CPU emulation");
+#else
+  namespace tc = pc::tc;
+  const tc::Geom g = tc::make_geom(P.Ppad, P.nblocks);
+  const size_t lines = (size_t)C * P.B;
+  if (!h->tc_err) {
+    CU_CHECK(h, cudaHostAlloc((void**)&h->tc_err, sizeof(int), cudaHostAllocMapped));
+    *h->tc_err = 0;
+    CU_CHECK(h, cudaHostGetDevicePointer((void**)&h->tc_err_dev, h->tc_err, 0));
+  }
+  if (*reinterpret_cast<volatile int*>(h->tc_err) != 0)
+    return fail(h, B200CONV_ECUDA, "tensor-core sweep: a pipeline barrier timed out (code " + std::to_string(*h->tc_err) + ")");
+  if (!tc_reserve(h, &h->tc_Xt, &h->tc_Xt_bytes, lines * 4 * (size_t)g.Lt * sizeof(float))) return 1;
+  if (!tc_reserve(h, &h->tc_Yt, &h->tc_Yt_bytes, lines * 4 * (size_t)g.Lty * sizeof(float))) return 1;
+  const size_t a_bytes = lines * (size_t)g.nchunk * 2 * tc::kATileBytes;
+  const bool a_stale = h->tc_A_for != P.H || h->tc_A_P != P.Ppad || h->tc_A_B != P.B || h->tc_A_C != C || h->tc_A_bytes < a_bytes;
+  if (a_stale) {
+    h->tc_A_for = nullptr;
+    if (!tc_reserve(h, &h->tc_A, &h->tc_A_bytes, a_bytes)) return 1;
+  }
+  if (!h->tc_attr_set) {
+    CU_CHECK(h, cudaFuncSetAttribute(tc::k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    h->tc_attr_set = true;
+  }
+  CUtensorMap tm;
+  if (tc::make_strip_tensor_map(&tm, h->tc_Xt, (unsigned long long)lines * 4ull * (unsigned long long)g.rows) != 0)
+    return fail(h, B200CONV_ECUDA, "cuTensorMapEncodeTiled failed");
+  cudaStream_t st = h->s_launch;
+  int id = timing_begin(h, kKindCmac);
+  if (a_stale) {     // once per IR (and stage): H -> tf32 hi / lo Toeplitz tile images
+    tc::BuildAParams bp{P.H, P.h_cstride, P.B, P.Ppad, g.Q, g.nchunk, h->tc_A};
+    tc::k_tc_build_a<<<dim3(g.nchunk, P.B, C), 256, 0, st>>>(bp);
+    h->tc_A_for = P.H; h->tc_A_P = P.Ppad; h->tc_A_B = P.B; h->tc_A_C = C;
+    h->launches++;
+  }
+  tc::SplitXParams sp{P.X, P.x_cstride, P.xrow0 - g.Q, std::max<long long>(0, P.xrow0 - (P.Ppad - 1)), P.xrow0 + P.nblocks, P.B, g.Lt, h->tc_Xt};
+  tc::k_tc_split_x<<<dim3((unsigned)(g.Lt / 32), P.B / 32, C), dim3(32, 8), 0, st>>>(sp);
+  tc::SweepParams wp{h->tc_A, h->tc_Yt, (int)lines, g.ntile, g.nchunk, g.rows, g.Lty, h->tc_err_dev};
+  const int total = (int)lines * g.ntile;
+  tc::k_tc_sweep<<<std::min(total, h->n_sm), tc::kThreads, tc::kSmemBytes, st>>>(tm, wp);
+  tc::MergeYParams mp{h->tc_Yt, g.Lty, P.B, P.nblocks, P.Y, P.y_cstride, P.y_rstride, P.yrow0};
+  tc::k_tc_merge_y<<<dim3((P.nblocks + 31) / 32, P.B / 32, C), dim3(32, 8), 0, st>>>(mp);
+  timing_end(h, id);
+  h->launches += 3;
+  CU_CHECK(h, cudaGetLastError());
+  return 0;
+#endif
+}
+
 // P.Ppad enters as the number of real (unpadded) partition rows of this shard
 int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
   int variant = h->cfg.cmac_variant;
@@ -654,7 +755,17 @@ int launch_cmac(b200conv* h, const pc::CmacParams& P, int C) {
     }
     else if (P.nblocks <= kStreamNBS && P.B >= 64 && P.Ppad >= 1) variant = 101;
     else if (P.nblocks <= kStreamNBS && P.B >= 2 && P.Ppad >= 1) variant = 100;
+    else if (h->opt_tc && !h->tc_alloc_failed && P.nblocks >= kTcMinBlocks && tc_eligible(h, P, C)) variant = 40;
     else variant = (P.nblocks >= 64) ? 22 : 26;
+  }
+  h->last_variant = variant;
+  if (variant == 40) {                         // tcgen05 3xTF32 block-Toeplitz sweep
+    if (!tc_eligible(h, P, C)) return fail(h, B200CONV_EINVAL, "tensor-core sweep: unsupported shape (needs B % 32 == 0, at most 961 partitions, no slot exchange)");
+    const int rc = launch_cmac_tc(h, P, C);
+    if (rc <= 0) return rc;
+    if (h->cfg.cmac_variant == 40) return fail(h, B200CONV_ENOMEM, "tensor-core sweep: scratch allocation failed");
+    variant = (P.nblocks >= 64) ? 22 : 26;     // not enough device memory for the scratch: FFMA sweep
+    h->last_variant = variant;
   }
   if (variant == 108) {                        // 6 stages x 2 CTAs/SM, skewed static slices (B200CONV_STREAM_SKEW percent, default 8)
     if (P.nblocks != 1 || P.B < 64) return fail(h, B200CONV_EINVAL, "TMA streaming sweep needs nblocks == 1 and B >= 64");
@@ -2389,6 +2500,8 @@ size_t b200conv_ir_len(const b200conv_t* h, int channel) {
 
 unsigned long long b200conv_launch_count(const b200conv_t* h) { return h ? h->launches : 0; }
 
+int b200conv_last_sweep_variant(const b200conv_t* h) { return h ? h->last_variant : 0; }
+
 int b200conv_set_option(b200conv_t* h, const char* name, int value) {
   if (!h || !name) return B200CONV_EINVAL;
   const std::string n(name);
@@ -2396,6 +2509,7 @@ int b200conv_set_option(b200conv_t* h, const char* name, int value) {
   else if (n == "fft512") h->opt_fft512 = value != 0;
   else if (n == "slice_keep_tail") h->opt_slice_tail = value != 0;
   else if (n == "stream_alternate") h->opt_stream_alt = value != 0;
+  else if (n == "tc") h->opt_tc = value != 0;
   else return fail(h, B200CONV_EINVAL, "unknown option");
   return B200CONV_OK;
 }

@@ -26,7 +26,7 @@
 // ring) stream during the tile.
 //
 // Kernels: k_tc_build_a (H -> tf32 hi/lo Toeplitz tile images, once per IR), k_tc_split_x (timeline rows -> per-bin
-// hi/lo time lines), k_tc_sweep (TMA producer warp / single-thread MMA issuer / 4 epilogue warps reading TMEM),
+// hi/lo time lines), k_tc_sweep (TMA producer warp / MMA warp with one elected issuing lane / 8 epilogue warps reading TMEM),
 // k_tc_merge_y (partial planes -> Y rows, combines the complex product).
 #pragma once
 
@@ -182,7 +182,7 @@ struct SweepParams {
   float* Yt;
   int lines, ntile, nchunk, rows;
   long long Lty;
-  int* err;                 // set non-zero when a barrier wait gave up (a bug, not a data condition)
+  int* err;                 // (mapped host word) set non-zero when a barrier wait gave up — a bug, not a data condition
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
       bool ok = true;
       for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++n) {
         const int line = tile / P.ntile, nt = tile - line * P.ntile;
-        if (n > 0 && !mbar_wait(&bar_strip_empty, (unsigned)(n - 1) & 1u)) { atomicExch(P.err, 1); break; }
+        if (n > 0 && !mbar_wait(&bar_strip_empty, (unsigned)(n - 1) & 1u)) { *reinterpret_cast<volatile int*>(P.err) = 1; break; }
         for (int e = 0; e < 2; ++e) {                     // plane e = 0 first: chunk 0 needs only that one
           mbar_expect(&bar_strip_full[e], 4 * kStripBytes);
           for (int pl = 0; pl < 4; ++pl)
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
         const float* Aline = P.A + (size_t)line * P.nchunk * 2 * 4096;
         for (int s = 0; s < P.nchunk * 2; ++s, ++it_a) {
           const unsigned stage = it_a % kAStages, use = it_a / kAStages;
-          if (use > 0 && !mbar_wait(&bar_a_empty[stage], (use - 1) & 1u)) { atomicExch(P.err, 2); ok = false; break; }
+          if (use > 0 && !mbar_wait(&bar_a_empty[stage], (use - 1) & 1u)) { *reinterpret_cast<volatile int*>(P.err) = 2; ok = false; break; }
           mbar_expect(&bar_a_full[stage], kATileBytes);
           bulk_load(ring + stage * kATileBytes, Aline + (size_t)s * 4096, kATileBytes, &bar_a_full[stage]);
         }
@@ -294,14 +294,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
       for (int c = 0; c < P.nchunk && ok; ++c) {
         const int g_in = c % kFlush;
         const uint32_t buf = gcount & 1u;
-        if (g_in == 0 && gcount >= 2 && !mbar_wait(&bar_tmem_empty[buf], ((gcount >> 1) - 1) & 1u)) { if (lane == 0) atomicExch(P.err, 4); ok = false; break; }
-        if (c < 2 && !mbar_wait(&bar_strip_full[c], (unsigned)n & 1u)) { if (lane == 0) atomicExch(P.err, 3); ok = false; break; }
+        if (g_in == 0 && gcount >= 2 && !mbar_wait(&bar_tmem_empty[buf], ((gcount >> 1) - 1) & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 4; ok = false; break; }
+        if (c < 2 && !mbar_wait(&bar_strip_full[c], (unsigned)n & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 3; ok = false; break; }
         const uint32_t e = (uint32_t)c & 1u, q = (uint32_t)c >> 1;
         const bool last_of_group = (g_in == kFlush - 1) || (c == P.nchunk - 1);
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl, ++it_a) {
           const unsigned stage = it_a % kAStages, use = it_a / kAStages;
-          if (!mbar_wait(&bar_a_full[stage], use & 1u)) { if (lane == 0) atomicExch(P.err, 5); ok = false; break; }
+          if (!mbar_wait(&bar_a_full[stage], use & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 5; ok = false; break; }
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_lo = ring_lo + stage * (kATileBytes >> 4);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
         for (int j = 0; j < 64; ++j) acc[comp][j] = 0.0f;
       for (int g = 0; g < ngroups; ++g, ++gcount) {
         const uint32_t buf = gcount & 1u;
-        if (!mbar_wait(&bar_tmem_full[buf], (gcount >> 1) & 1u)) { if (lane == 0) atomicExch(P.err, 6); ok = false; break; }
+        if (!mbar_wait(&bar_tmem_full[buf], (gcount >> 1) & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 6; ok = false; break; }
         tc_fence_after();
 #pragma unroll
         for (int comp = 0; comp < 2; ++comp) {

@@ -208,6 +208,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                :: "r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
@@ -274,6 +277,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
           mbar_expect(&bar_strip_full[e], 4 * kStripBytes);
           for (int pl = 0; pl < 4; ++pl)
             tma_load_2d(strips + (pl * 2 + e) * kStripBytes, &tmX, 32 * e, (line * 4 + pl) * P.rows + nt * kN, &bar_strip_full[e]);
+        }
+        if (tile + (int)gridDim.x < total) {              // the next tile's strips: into L2 now, so that the loads at the
+          const int t2 = tile + (int)gridDim.x, l2 = t2 / P.ntile, n2 = t2 - l2 * P.ntile;   // tile boundary do not wait for HBM
+          for (int e = 0; e < 2; ++e)
+            for (int pl = 0; pl < 4; ++pl) tma_prefetch_2d(&tmX, 32 * e, (l2 * 4 + pl) * P.rows + n2 * kN);
         }
         const float* Aline = P.A + (size_t)line * P.nchunk * 2 * 4096;
         for (int s = 0; s < P.nchunk * 2; ++s, ++it_a) {

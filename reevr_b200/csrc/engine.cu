@@ -714,9 +714,6 @@ int launch_cmac_tc(b200conv* h, const pc::CmacParams& P, int C) {
     CU_CHECK(h, cudaFuncSetAttribute(tc::k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
     h->tc_attr_set = true;
   }
-  CUtensorMap tm;
-  if (tc::make_strip_tensor_map(&tm, h->tc_Xt, (unsigned long long)lines * 4ull * (unsigned long long)g.rows) != 0)
-    return fail(h, B200CONV_ECUDA, "cuTensorMapEncodeTiled failed");
   cudaStream_t st = h->s_launch;
   int id = timing_begin(h, kKindCmac);
   if (a_stale) {     // once per IR (and stage): H -> tf32 hi / lo Toeplitz tile images
@@ -725,11 +722,11 @@ int launch_cmac_tc(b200conv* h, const pc::CmacParams& P, int C) {
     h->tc_A_for = P.H; h->tc_A_P = P.Ppad; h->tc_A_B = P.B; h->tc_A_C = C;
     h->launches++;
   }
-  tc::SplitXParams sp{P.X, P.x_cstride, P.xrow0 - g.Q, std::max<long long>(0, P.xrow0 - (P.Ppad - 1)), P.xrow0 + P.nblocks, P.B, g.Lt, h->tc_Xt};
-  tc::k_tc_split_x<<<dim3((unsigned)(g.Lt / 32), P.B / 32, C), dim3(32, 8), 0, st>>>(sp);
-  tc::SweepParams wp{h->tc_A, h->tc_Yt, (int)lines, g.ntile, g.nchunk, g.rows, g.Lty, h->tc_err_dev};
+  tc::SplitXParams sp{P.X, P.x_cstride, P.xrow0 - g.Q, std::max<long long>(0, P.xrow0 - (P.Ppad - 1)), P.xrow0 + P.nblocks, P.B, g.rows, h->tc_Xt};
+  tc::k_tc_split_x<<<dim3((unsigned)(g.rows * 2), P.B / 32, C), dim3(32, 8), 0, st>>>(sp);
+  tc::SweepParams wp{h->tc_A, h->tc_Xt, h->tc_Yt, (int)lines, g.ntile, g.nchunk, g.rows, g.Lty, 0, h->tc_err_dev};
   const int total = (int)lines * g.ntile;
-  tc::k_tc_sweep<<<std::min(total, h->n_sm), tc::kThreads, tc::kSmemBytes, st>>>(tm, wp);
+  tc::k_tc_sweep<<<std::min(total, h->n_sm), tc::kThreads, tc::kSmemBytes, st>>>(wp);
   tc::MergeYParams mp{h->tc_Yt, g.Lty, P.B, P.nblocks, P.Y, P.y_cstride, P.y_rstride, P.yrow0};
   tc::k_tc_merge_y<<<dim3((P.nblocks + 31) / 32, P.B / 32, C), dim3(32, 8), 0, st>>>(mp);
   timing_end(h, id);

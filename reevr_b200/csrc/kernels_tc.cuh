@@ -21,7 +21,7 @@
 // of plane c%2, i.e. the same strip with the descriptor start address advanced by (c/2) * 128 bytes — the
 // hardware applies the 128-byte swizzle to absolute address bits, so a start address inside the 1024-byte swizzle
 // atom is fine (tools/tc_probe.cu, profiles/r02_tc_probe.txt).  One 144-row strip per plane (8 planes: re/im x
-// hi/lo x e, 147 KB, one TMA tile load each) feeds all 32 K chunks of a 128-segment tile: every x sample enters
+// hi/lo x e, 147 KB, one 1-D bulk copy each: the global time lines are stored as pre-swizzled strip images) feeds all 32 K chunks of a 128-segment tile: every x sample enters
 // shared memory once, and only the Toeplitz tiles of H (16 KB, pre-swizzled images, 1-D bulk copies through a 4-stage
 // ring) stream during the tile.
 //
@@ -30,7 +30,6 @@
 // k_tc_merge_y (partial planes -> Y rows, combines the complex product).
 #pragma once
 
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -109,17 +108,25 @@ __global__ void __launch_bounds__(256) k_tc_build_a(BuildAParams p) {
 }
 
 // ---- timeline rows -> per-bin hi / lo time lines ---------------------------------------------------------------
+// Xt layout: [line][re_hi, re_lo, im_hi, im_lo][e][row R][32 floats], the sample tau = 64 R + 32 e + jj stored at
+// 16-byte chunk (jj / 4) ^ (R % 8) of its 128-byte row: a strip (kStripRows consecutive rows of one plane, first row a
+// multiple of 8) is ONE contiguous 18 KB piece of global memory that is already the SWIZZLE_128B shared-memory image,
+// so the sweep fetches it with a single 1-D bulk copy (no tensor map, no per-row TMA requests).
+inline __host__ __device__ size_t xt_index(long long line, int pl, int e, long long R, int jj, int rows) {
+  return ((((size_t)line * 4 + pl) * 2 + e) * (size_t)rows + (size_t)R) * 32 + (size_t)(((((jj >> 2) ^ (int)(R & 7)) & 7) << 2) | (jj & 3));
+}
+
 struct SplitXParams {
   const float2* X;          // [C][R][B]
   long long x_cstride;
   long long row_base;       // timeline row of tau = 0 (= row of output block 0 minus Q); may be negative
   long long row_lo, row_hi; // rows outside [row_lo, row_hi) read as zero
   int B;
-  long long Lt;
-  float* Xt;                // [C*B lines][re_hi, re_lo, im_hi, im_lo][Lt]
+  int rows;                 // 64-sample rows per plane
+  float* Xt;
 };
 
-// grid (Lt / 32, B / 32, C), block (32, 8)
+// grid (rows * 2, B / 32, C), block (32, 8)
 __global__ void __launch_bounds__(256) k_tc_split_x(SplitXParams p) {
   __shared__ float2 tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -132,15 +139,16 @@ __global__ void __launch_bounds__(256) k_tc_split_x(SplitXParams p) {
     tile[r][tx] = v;
   }
   __syncthreads();
+  const long long R = tau0 >> 6;
+  const int e = (int)((tau0 >> 5) & 1);
   for (int kk = ty; kk < 32; kk += 8) {
     const float2 v = tile[tx][kk];
     const long long line = (long long)ch * p.B + k0 + kk;
-    float* dst = p.Xt + line * 4 * p.Lt + tau0 + tx;
     const float rh = tf32_rn(v.x), ih = tf32_rn(v.y);
-    dst[0] = rh;
-    dst[p.Lt] = tf32_rn(v.x - rh);
-    dst[2 * p.Lt] = ih;
-    dst[3 * p.Lt] = tf32_rn(v.y - ih);
+    p.Xt[xt_index(line, 0, e, R, tx, p.rows)] = rh;
+    p.Xt[xt_index(line, 1, e, R, tx, p.rows)] = tf32_rn(v.x - rh);
+    p.Xt[xt_index(line, 2, e, R, tx, p.rows)] = ih;
+    p.Xt[xt_index(line, 3, e, R, tx, p.rows)] = tf32_rn(v.y - ih);
   }
 }
 
@@ -179,9 +187,11 @@ __global__ void __launch_bounds__(256) k_tc_merge_y(MergeYParams p) {
 // ---- the sweep -------------------------------------------------------------------------------------------------
 struct SweepParams {
   const float* A;
+  const float* Xt;
   float* Yt;
   int lines, ntile, nchunk, rows;
   long long Lty;
+  int dbg;                  // timing experiments only (tools/tc_sweep_test.cu): 1 no Yt stores, 2 strips loaded once, 4 A ring loaded once
   int* err;                 // (mapped host word) set non-zero when a barrier wait gave up — a bug, not a data condition
 };
 
@@ -208,13 +218,6 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               :: "r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
-}
 // SWIZZLE_128B K-major operand descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart), split in two words:
 // only the low word (start address in 16-byte units | leading-offset field) changes between MMAs
 constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -240,7 +243,7 @@ __device__ __forceinline__ bool elect_one() {
 // of kFlush chunks and hands it to the epilogue warps, which add it to FP32 registers (round-to-nearest) while the
 // other buffer fills: the tensor core's accumulate truncates, so short accumulation chains keep the error at the
 // level of the FFMA sweep, and the epilogue of a tile overlaps the MMAs of the next one.
-__global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant__ CUtensorMap tmX, SweepParams P) {
+__global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(SweepParams P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* strips = base;                           // [comp][hi, lo][e] x kStripBytes
@@ -272,20 +275,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
       bool ok = true;
       for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++n) {
         const int line = tile / P.ntile, nt = tile - line * P.ntile;
-        if (n > 0 && !mbar_wait(&bar_strip_empty, (unsigned)(n - 1) & 1u)) { *reinterpret_cast<volatile int*>(P.err) = 1; break; }
-        for (int e = 0; e < 2; ++e) {                     // plane e = 0 first: chunk 0 needs only that one
+        const bool load_strips = !(P.dbg & 2) || n == 0;
+        if (load_strips && n > 0 && !mbar_wait(&bar_strip_empty, (unsigned)(n - 1) & 1u)) { *reinterpret_cast<volatile int*>(P.err) = 1; break; }
+        for (int e = 0; e < 2 && load_strips; ++e) {      // plane e = 0 first: chunk 0 needs only that one
           mbar_expect(&bar_strip_full[e], 4 * kStripBytes);
           for (int pl = 0; pl < 4; ++pl)
-            tma_load_2d(strips + (pl * 2 + e) * kStripBytes, &tmX, 32 * e, (line * 4 + pl) * P.rows + nt * kN, &bar_strip_full[e]);
-        }
-        if (tile + (int)gridDim.x < total) {              // the next tile's strips: into L2 now, so that the loads at the
-          const int t2 = tile + (int)gridDim.x, l2 = t2 / P.ntile, n2 = t2 - l2 * P.ntile;   // tile boundary do not wait for HBM
-          for (int e = 0; e < 2; ++e)
-            for (int pl = 0; pl < 4; ++pl) tma_prefetch_2d(&tmX, 32 * e, (l2 * 4 + pl) * P.rows + n2 * kN);
+            bulk_load(strips + (pl * 2 + e) * kStripBytes, P.Xt + ((((size_t)line * 4 + pl) * 2 + e) * (size_t)P.rows + (size_t)nt * kN) * 32, kStripBytes,
+                      &bar_strip_full[e]);
         }
         const float* Aline = P.A + (size_t)line * P.nchunk * 2 * 4096;
         for (int s = 0; s < P.nchunk * 2; ++s, ++it_a) {
           const unsigned stage = it_a % kAStages, use = it_a / kAStages;
+          if ((P.dbg & 4) && use > 0) continue;
           if (use > 0 && !mbar_wait(&bar_a_empty[stage], (use - 1) & 1u)) { *reinterpret_cast<volatile int*>(P.err) = 2; ok = false; break; }
           mbar_expect(&bar_a_full[stage], kATileBytes);
           bulk_load(ring + stage * kATileBytes, Aline + (size_t)s * 4096, kATileBytes, &bar_a_full[stage]);
@@ -303,13 +304,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
         const int g_in = c % kFlush;
         const uint32_t buf = gcount & 1u;
         if (g_in == 0 && gcount >= 2 && !mbar_wait(&bar_tmem_empty[buf], ((gcount >> 1) - 1) & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 4; ok = false; break; }
-        if (c < 2 && !mbar_wait(&bar_strip_full[c], (unsigned)n & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 3; ok = false; break; }
+        if (c < 2 && (!(P.dbg & 2) || n == 0) && !mbar_wait(&bar_strip_full[c], (unsigned)n & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 3; ok = false; break; }
         const uint32_t e = (uint32_t)c & 1u, q = (uint32_t)c >> 1;
         const bool last_of_group = (g_in == kFlush - 1) || (c == P.nchunk - 1);
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl, ++it_a) {
           const unsigned stage = it_a % kAStages, use = it_a / kAStages;
-          if (!mbar_wait(&bar_a_full[stage], use & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 5; ok = false; break; }
+          if ((!(P.dbg & 4) || use == 0) && !mbar_wait(&bar_a_full[stage], use & 1u)) { if (lane == 0) *reinterpret_cast<volatile int*>(P.err) = 5; ok = false; break; }
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_lo = ring_lo + stage * (kATileBytes >> 4);
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
         if (lane == 0) mbar_arrive1(&bar_tmem_empty[buf]);
       }
       if (!ok) break;
+      if (P.dbg & 1) continue;
 #pragma unroll
       for (int comp = 0; comp < 2; ++comp) {
         float* dst = P.Yt + ((size_t)line * 4 + comp * 2 + part) * P.Lty + ((size_t)nt * kN + half * 64) * 64 + i;
@@ -388,28 +390,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_sweep(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
-}
-
-// ---- host helpers ----------------------------------------------------------------------------------------------
-// tensor map over Xt seen as rows of 64 floats: box = 32 floats x kStripRows rows, SWIZZLE_128B
-inline int make_strip_tensor_map(CUtensorMap* tm, const float* Xt, unsigned long long total_rows) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-      return -1;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  const cuuint64_t gdim[2] = {64, (cuuint64_t)total_rows};
-  const cuuint64_t gstride[1] = {256};
-  const cuuint32_t box[2] = {32, (cuuint32_t)kStripRows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Xt), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -2;
 }
 
 #endif  // __CUDACC__

@@ -160,13 +160,14 @@ int main() {
         if (!good && mode == 0 && q == 0) ++failures;
       }
   for (int N : {128, 256}) {
-    for (int iters : {256, 2048}) {
+    for (int q : {0, 1, 4, 8, 13})
+    for (int iters : {2048}) {
       CK(cudaMemset(dst, 0, 4));
-      ProbeParams P{dA, dX, dD, N, strip_rows, 0, 0, iters, dcyc, dst};
+      ProbeParams P{dA, dX, dD, N, strip_rows, q, 0, iters, dcyc, dst};
       k_probe<<<1, 128, smem>>>(P);
       CK(cudaDeviceSynchronize());
       long long cyc = 0; CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
-      std::printf("timing N=%3d: %d x 4 MMAs (128 x %d x 8 tf32, SS) in %lld cycles = %.1f cycles per MMA\n", N, iters, N, cyc, (double)cyc / (iters * 4.0));
+      std::printf("timing N=%3d window shift q=%2d: %d x 4 MMAs (128 x %d x 8 tf32, SS) in %lld cycles = %.1f cycles per MMA\n", N, q, iters, N, cyc, (double)cyc / (iters * 4.0));
     }
   }
   std::printf(failures ? "PROBE FAILED\n" : "PROBE DONE\n");

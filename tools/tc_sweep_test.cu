@@ -43,23 +43,21 @@ static int run_case(int C, int B, int P, int nb, int grid, int reps) {
   CK(cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dY, 0xFF, (size_t)(nb + 1) * C * B * 8));
   CK(cudaMemset(dYt, 0xFF, lines * 4 * g.Lty * 4));
-  CUtensorMap tm;
-  if (int rc = make_strip_tensor_map(&tm, dXt, (unsigned long long)lines * 4 * g.rows)) { std::printf("tensor map failed %d\n", rc); return 2; }
   CK(cudaFuncSetAttribute(k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaEvent_t ev[5];
   for (auto& e : ev) CK(cudaEventCreate(&e));
   BuildAParams bp{dH, (long long)P * B, B, P, g.Q, g.nchunk, dA};
-  SplitXParams sp{dX, R * B, xrow0 - g.Q, row_lo, R, B, g.Lt, dXt};
-  SweepParams wp{dA, dYt, (int)lines, g.ntile, g.nchunk, g.rows, g.Lty, derr};
+  SplitXParams sp{dX, R * B, xrow0 - g.Q, row_lo, R, B, g.rows, dXt};
+  SweepParams wp{dA, dXt, dYt, (int)lines, g.ntile, g.nchunk, g.rows, g.Lty, 0, derr};
   MergeYParams mp{dYt, g.Lty, B, nb, dY, (long long)B, (long long)C * B, 1};
   float best[4] = {1e30f, 1e30f, 1e30f, 1e30f};
   for (int rep = 0; rep < reps; ++rep) {
     CK(cudaEventRecord(ev[0]));
     k_tc_build_a<<<dim3(g.nchunk, B, C), 256>>>(bp);
     CK(cudaEventRecord(ev[1]));
-    k_tc_split_x<<<dim3((unsigned)(g.Lt / 32), B / 32, C), dim3(32, 8)>>>(sp);
+    k_tc_split_x<<<dim3((unsigned)(g.rows * 2), B / 32, C), dim3(32, 8)>>>(sp);
     CK(cudaEventRecord(ev[2]));
-    k_tc_sweep<<<grid, kThreads, kSmemBytes>>>(tm, wp);
+    k_tc_sweep<<<grid, kThreads, kSmemBytes>>>(wp);
     CK(cudaEventRecord(ev[3]));
     k_tc_merge_y<<<dim3((nb + 31) / 32, B / 32, C), dim3(32, 8)>>>(mp);
     CK(cudaEventRecord(ev[4]));
@@ -72,6 +70,26 @@ static int run_case(int C, int B, int P, int nb, int grid, int reps) {
   const double macs = 4.0 * P * (double)nb * B * C;     // real FMAs of the direct form
   std::printf("  build_a %.3f ms | split_x %.3f ms | sweep %.3f ms (%.1f TFLOP/s direct-form equivalent) | merge_y %.3f ms | barrier status %d\n", best[0], best[1],
               best[2], 2.0 * macs / (best[2] * 1e-3) / 1e12, best[3], err);
+  if (std::getenv("TC_EXPERIMENTS")) {                  // where does the time go?  (results of these runs are not valid outputs)
+    for (int dbg : {1, 2, 4, 6, 7}) {
+      SweepParams we = wp;
+      we.dbg = dbg;
+      float bestd = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(ev[0]));
+        k_tc_sweep<<<grid, kThreads, kSmemBytes>>>(we);
+        CK(cudaEventRecord(ev[1]));
+        CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); bestd = std::fmin(bestd, ms);
+      }
+      std::printf("  experiment dbg=%d (%s%s%s): sweep %.3f ms\n", dbg, (dbg & 1) ? "no Yt stores " : "", (dbg & 2) ? "strips loaded once " : "",
+                  (dbg & 4) ? "A ring loaded once" : "", bestd);
+    }
+    CK(cudaMemset(derr, 0, 4));
+    k_tc_sweep<<<grid, kThreads, kSmemBytes>>>(wp);   // restore valid planes for the check below
+    k_tc_merge_y<<<dim3((nb + 31) / 32, B / 32, C), dim3(32, 8)>>>(mp);
+    CK(cudaDeviceSynchronize());
+  }
   std::vector<float2> Y((size_t)(nb + 1) * C * B);
   CK(cudaMemcpy(Y.data(), dY, Y.size() * 8, cudaMemcpyDeviceToHost));
   double worst = 0, peak = 0;

@@ -26,6 +26,11 @@ KEYS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "smsp__sass_inst_executed_op_utcmma.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 

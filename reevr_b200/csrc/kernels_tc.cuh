@@ -70,6 +70,14 @@ inline __host__ __device__ bool geom_ok(const Geom& g, int B) { return g.nchunk 
 // byte offset of element (row r, float e < 32) in a SWIZZLE_128B K-major image with a 1024-byte aligned base
 inline __host__ __device__ uint32_t sw128(uint32_t r, uint32_t e) { return r * 128u + ((((e >> 2) ^ (r & 7u)) & 7u) << 4) + (e & 3u) * 4u; }
 
+// Xt layout: [line][re_hi, re_lo, im_hi, im_lo][e][row R][32 floats], the sample tau = 64 R + 32 e + jj stored at
+// 16-byte chunk (jj / 4) ^ (R % 8) of its 128-byte row: a strip (kStripRows consecutive rows of one plane, first row a
+// multiple of 8) is ONE contiguous 18 KB piece of global memory that is already the SWIZZLE_128B shared-memory image,
+// so the sweep fetches it with a single 1-D bulk copy (no tensor map, no per-row TMA requests).
+inline __host__ __device__ size_t xt_index(long long line, int pl, int e, long long R, int jj, int rows) {
+  return ((((size_t)line * 4 + pl) * 2 + e) * (size_t)rows + (size_t)R) * 32 + (size_t)(((((jj >> 2) ^ (int)(R & 7)) & 7) << 2) | (jj & 3));
+}
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,14 +116,6 @@ __global__ void __launch_bounds__(256) k_tc_build_a(BuildAParams p) {
 }
 
 // ---- timeline rows -> per-bin hi / lo time lines ---------------------------------------------------------------
-// Xt layout: [line][re_hi, re_lo, im_hi, im_lo][e][row R][32 floats], the sample tau = 64 R + 32 e + jj stored at
-// 16-byte chunk (jj / 4) ^ (R % 8) of its 128-byte row: a strip (kStripRows consecutive rows of one plane, first row a
-// multiple of 8) is ONE contiguous 18 KB piece of global memory that is already the SWIZZLE_128B shared-memory image,
-// so the sweep fetches it with a single 1-D bulk copy (no tensor map, no per-row TMA requests).
-inline __host__ __device__ size_t xt_index(long long line, int pl, int e, long long R, int jj, int rows) {
-  return ((((size_t)line * 4 + pl) * 2 + e) * (size_t)rows + (size_t)R) * 32 + (size_t)(((((jj >> 2) ^ (int)(R & 7)) & 7) << 2) | (jj & 3));
-}
-
 struct SplitXParams {
   const float2* X;          // [C][R][B]
   long long x_cstride;

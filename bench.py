@@ -14,10 +14,14 @@ at every N ("strong" scaling).
                    engine's stream, max over ranks, L2 flushed between steps.
 * e2e              same metric through the host-pointer C ABI with pinned HOST buffers (H2D + D2H in
                    the timed region, wall clock around the synchronous call, max over ranks).
-* roofline         dominant kernel k_cmac_batch2 (FDL sweep).  The batched sweep keeps every H[p][k] in
-                   registers for 16 blocks, so it is bound by FP32 FMA issue, not by HBM: the primary
-                   entry is FP32 TFLOP/s vs 148 SM x 128 lanes x 2 x sm_max_mhz; the SURVEY §8(d)
-                   algorithmic-bytes ratio (> 1 by construction) is the labelled secondary `hbm_algorithmic`.
+* roofline         dominant kernel = the FDL sweep in the form the engine chose (b200conv_last_sweep_variant):
+                   - k_tc_sweep (launch groups >= 4096 blocks, P <= 961 — the metric shape): tcgen05 kind::tf32 block-Toeplitz
+                     GEMMs with the 3xTF32 split; bound "tensor": EXECUTED tf32 flops / the whole sweep stage (time lines +
+                     MMAs + merge) vs half the measured bf16 rate of MEASURED_PEAKS.json; the direct-form-equivalent FP32 rate
+                     against the CUDA-core FMA peak is the labelled secondary `useful_fp32_equivalent`;
+                   - k_cmac_batch2 (--variant 22, shorter groups, longer IRs): every H[p][k] stays in registers for 16
+                     blocks, bound "fp32": FP32 TFLOP/s vs 148 SM x 128 lanes x 2 x sm_max_mhz.
+                   The SURVEY 8(d) algorithmic-bytes ratio (> 1 by construction) is the labelled secondary `hbm_algorithmic`.
                    `traffic` = dram bytes of one launch from a LIVE ncu capture of this very script
                    (--probe mode, subprocess), null when ncu / the counters are not available.
 * roofline_stream  the memory-bound form of the same sweep (one block per launch, 120 s IR, working set
@@ -986,6 +990,9 @@ def main():
             "config": main_res["config"], "clocks": main_res["clocks"], "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches"], "roofline": main_res["roofline"], "cpu_baseline": cpu,
             "parity": main_res["parity"],
+            "arithmetic": ("FP32 results from tf32 tensor-core products: 3xTF32 split (hi*hi + hi*lo + lo*hi), FP32 accumulate, "
+                           "chains of 48 MMAs folded into FP32 registers; same 1e-5 parity bar (see parity)"
+                           if main_res["roofline"].get("bound") == "tensor" else "FP32 FMA (packed FFMA2)"),
         }
         if extra:
             line["ir120"] = extra

@@ -41,7 +41,8 @@ typedef struct b200conv_config {
   int max_batch_blocks;  /* head-stage blocks processed per internal launch group (0 = default 4736) */
   int shard_rank;        /* partition-range shard owned by this handle (multi-GPU), 0 <= rank < n   */
   int shard_count;       /* number of shards (1 = unsharded)                                        */
-  int cmac_variant;      /* 0 = auto; >0 selects a specific CMAC kernel variant (tuning/bench)      */
+  int cmac_variant;      /* 0 = auto; >0 selects a specific CMAC kernel variant (tuning/bench):     */
+                         /* 22 packed-FMA batched, 40 tensor cores (tcgen05), 100..108 streaming    */
 } b200conv_config;
 
 /* Lifetime ------------------------------------------------------------------------------- */
@@ -120,7 +121,9 @@ int b200conv_last_sweep_variant(const b200conv_t* h);
  * "slice_keep_tail" (default 1; 0 = b200conv_process_sliced does not upload / transform the last P blocks of the call:
  * the handle then only supports a following sliced call whose slice starts >= P blocks into the call — every rank
  * but 0 of a steady batch job — until the next b200conv_clear), "stream_alternate" (default 1: the streaming sweep
- * walks its partition slices in alternating directions from launch to launch, see kernels_stream.cuh). */
+ * walks its partition slices in alternating directions from launch to launch, see kernels_stream.cuh), "tc" (default 1:
+ * launch groups of >= 4096 blocks with <= 961 partitions run the sweep on the tensor cores, kernels_tc.cuh; 0 = always
+ * the packed-FMA sweep). */
 int    b200conv_set_option(b200conv_t* h, const char* name, int value);
 /* Device time (ms) spent in the dominant CMAC kernel / all kernels during the last
  * b200conv_process_device call, measured with CUDA events on the handle's stream

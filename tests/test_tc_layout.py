@@ -126,3 +126,19 @@ def test_float64_model_of_the_tiled_sweep(shim, P, nb):
             hs, xs = H[line], x[line, xrow0 + t - np.arange(P)]
             ref = complex(np.sum(hs.real * xs.real), np.sum(hs.imag * xs.imag)) if line == 0 else np.sum(hs * xs)
             assert abs(y[line, t] - ref) <= 1e-9 * max(1.0, abs(ref)), (line, t)
+
+
+def test_bench_flop_model_matches_the_kernel_geometry(shim):
+    """bench.py's tensor roofline counts tiles x K chunks x 24 MMAs x 2*128*128*8 executed flops per launch; the tile and
+    chunk counts it derives from (P, blocks per launch) must be the kernel's own (make_geom)."""
+    k = consts(shim)
+    for P, nb, C, B in [(938, 112608, 2, 512), (938, 14077, 2, 512), (100, 4608, 2, 64), (961, 8192, 4, 256)]:
+        g = geom(shim, P, nb)
+        q = (max(P - 1, 0) + 63) // 64 * 64                                # bench.py: sweep_roofline()
+        nchunk = q // 32 + 2
+        ntile = -(-(-(-nb // 64)) // 128)
+        assert (nchunk, ntile) == (g["nchunk"], g["ntile"])
+        per_stage_mmas = 16 + 8                                              # hi image: 4 k-steps x 2 time lines x 2 products, lo image: x 1
+        flop = C * B * ntile * nchunk * per_stage_mmas * 2.0 * 128 * k["N"] * 8
+        if (P, nb, C, B) == (938, 112608, 2, 512):
+            assert flop == 2886218022912.0                                   # the figure in profiles/r02_bench_n1.json
